@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE ONLY -- generate golden vectors from the *real* reference.
+
+Run in the build container (``/root/reference`` mounted):
+
+    python oracle/make_golden.py [micro cfg1 cfg2]
+
+For each workload it instantiates the reference's own ``Lily`` (lily.py:23) on the reference's own
+``BertConfig`` (vilbert/vilbert.py:129), loads the name-keyed synthetic weights of ``yvb200.synth``,
+runs ``model.eval()`` forward through the reference's ``get_model_input`` (utils/utils_init.py:34),
+evaluates the four losses with the reference's ``get_loss_correct`` (utils/utils_init.py:108) in the
+``training=True`` branch, sums them like ``train_epoch`` (utils/utils_init.py:217-224), calls
+``loss.backward()`` and stores:
+
+  micro : complete outputs + complete gradients (narrow model, a few hundred KB)
+  cfg1/2: ranking/traj logits, the loss scalars, and for the big tensors (vision / language outputs,
+          every parameter gradient) the L2 norm plus values at seeded sample positions.
+
+The files land in ``tests/golden/<workload>.npz`` and are committed; the GPU box never needs
+``/root/reference``.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "youtube-vln_b200"))
+sys.path.insert(0, HERE)
+
+from yvb200 import synth  # noqa: E402
+import refload  # noqa: E402
+
+N_SAMPLE_OUT = 4096
+N_SAMPLE_GRAD = 64
+
+
+def sample_positions(name: str, numel: int, k: int) -> np.ndarray:
+    g = torch.Generator().manual_seed(synth._seed_of("sample:" + name, 7))
+    if numel <= k:
+        return np.arange(numel, dtype=np.int64)
+    return torch.randint(0, numel, (k,), generator=g).numpy().astype(np.int64)
+
+
+def run(workload: str):
+    vb, lily, ui = refload.load_reference()
+    w = synth.WORKLOADS[workload]
+    cfgd = synth.CONFIGS[w["config"]]
+    args = synth.workload_args(workload)
+    config = vb.BertConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in cfgd.items()})
+    config.args = args
+    torch.manual_seed(0)
+    model = lily.Lily(config)
+    synth.load_synthetic_weights(model, seed=0)
+    model.eval()
+    batch = synth.make_batch(workload, seed=1)
+    t0 = time.time()
+    outputs = model(*ui.get_model_input(tuple(batch)))
+    total = 0.0
+    loss_vals = {}
+    for task in ("vision", "language", "ranking", "traj"):
+        _, _, loss, _ = ui.get_loss_correct(tuple(batch), outputs, task, args, None, True)
+        loss_vals[task] = float(loss.detach())
+        total = total + (args.traj_loss_scale * loss if task == "traj" else loss)
+    model.zero_grad()
+    total.backward()
+    dt = time.time() - t0
+    out = {"total_loss": np.float64(float(total.detach())), "ref_seconds": np.float64(dt)}
+    for k, v in loss_vals.items():
+        out["loss/" + k] = np.float64(v)
+    full = workload == "micro"
+    for k, v in outputs.items():
+        a = v.detach().float().numpy()
+        if full or a.size <= N_SAMPLE_OUT:
+            out["out/" + k] = a
+        else:
+            pos = sample_positions("out/" + k, a.size, N_SAMPLE_OUT)
+            out["outpos/" + k] = pos
+            out["outval/" + k] = a.reshape(-1)[pos]
+            out["outnorm/" + k] = np.float64(np.linalg.norm(a.astype(np.float64)))
+    n_grad = 0
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            out["nograd/" + name] = np.int8(1)
+            continue
+        gr = p.grad.detach().float().numpy()
+        n_grad += 1
+        if full:
+            out["grad/" + name] = gr
+        else:
+            pos = sample_positions("grad/" + name, gr.size, N_SAMPLE_GRAD)
+            out["gradpos/" + name] = pos
+            out["gradval/" + name] = gr.reshape(-1)[pos]
+            out["gradnorm/" + name] = np.float64(np.linalg.norm(gr.astype(np.float64)))
+    path = os.path.join(ROOT, "tests", "golden", f"{workload}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{workload}: total_loss={float(total):.6f} losses={loss_vals} params_with_grad={n_grad} "
+          f"ref fwd+bwd {dt:.1f}s -> {path} ({os.path.getsize(path)/1e3:.0f} KB)")
+
+
+if __name__ == "__main__":
+    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2"]):
+        run(wl)
