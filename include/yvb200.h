@@ -1,0 +1,158 @@
+/* yvb200 -- C ABI of the B200-native ViLBERT hot path (libyvb200.so).
+ *
+ * The reference (JeremyLinky/YouTube-VLN) is pure Python on top of torch ATen; it has no FFI of its own.
+ * The boundary it would bind for this path is therefore the set of operators that vilbert/vilbert.py
+ * composes; each entry point below names the reference lines it replaces.  All pointers are DEVICE
+ * pointers owned by the caller (PyTorch's caching allocator on the host side); the library never
+ * allocates or frees device memory, never synchronises, and enqueues everything on `stream`.
+ * Return value: 0 on success, non-zero on error with a message available from yv_last_error().
+ *
+ * Number formats
+ *   f32       : row-major float matrices [rows, ld]
+ *   "planes"  : a GEMM operand is two bf16 matrices, plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi).
+ *               passes == 3 contracts hi*hi + hi*lo + lo*hi in fp32 (the "bf16x3" parity mode, ~2^-16
+ *               relative operand error); passes == 1 uses the hi planes only (plain bf16).
+ */
+#ifndef YVB200_H
+#define YVB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* yv_stream_t; /* cudaStream_t */
+
+const char* yv_last_error(void);
+int yv_version(void);
+/* kernels launched by this library since load (evidence for bench.py's "gpu_launches") */
+uint64_t yv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * yv_gemm: D = epilogue(alpha * A.B^T)  on tcgen05 tensor cores (TMA-staged 128x128x64 tiles, TMEM accum)
+ * replaces every nn.Linear / torch.matmul on the path: vilbert/vilbert.py:285-287,294,306,322,352,365,
+ * 414-416,423,435,450,479,492,555-573,577,591,597,613,641,644,831,846,864,883,906,968,1358 and their
+ * autograd dgrad / wgrad twins.
+ * An operand is a (possibly batched, possibly transposed) view of a bf16 plane pair:
+ *   mn_major == 0: element (r, k) at ptr[r*ld + k]          (rows index M or N, `inner` is K)
+ *   mn_major == 1: element (r, k) at ptr[k*ld + r]          (rows index K, `inner` is M or N)
+ * batch z = b1*nb0 + b0 adds b0*sb0 + b1*sb1; the lo plane sits plane_stride elements after hi.
+ * ld, sb0, sb1, plane_stride must be multiples of 8 elements and ptr 16-byte aligned (TMA).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* ptr;
+    int64_t inner, rows, ld;
+    int64_t nb0, sb0, nb1, sb1;
+    int64_t plane_stride;
+    int32_t mn_major, _pad;
+} YvOperand;
+
+enum { YV_ACT_NONE = 0, YV_ACT_GELU = 1, YV_ACT_RELU = 2, YV_ACT_MUL_GELU_GRAD = 3, YV_ACT_MUL_RELU_MASK = 4 };
+
+typedef struct {
+    int32_t M, N, K, passes;      /* passes: 1 (bf16) or 3 (bf16x3) */
+    YvOperand a, b;
+    float alpha;
+    int32_t act;
+    const float* bias;            /* [N] or NULL */
+    float* aux_out;               /* optional: pre-activation (alpha*acc + bias) saved for backward */
+    const float* aux_in;          /* MUL_GELU_GRAD: pre-activation; MUL_RELU_MASK: forward output */
+    const float* residual;        /* optional f32 addend (may alias out32 -> accumulate) */
+    float* out32;                 /* optional f32 output */
+    int64_t ld_out, out_sb0, out_sb1; /* layout shared by out32 / aux_out / aux_in / residual */
+    void* out_planes;             /* optional bf16 plane-pair output */
+    int64_t ld_pl, pl_sb0, pl_sb1, pl_plane_stride;
+    float drop_p;                 /* dropout after the activation, before the residual add */
+    uint32_t drop_site;
+    const uint64_t* rng;          /* device {seed, step}; NULL or drop_p == 0 disables dropout */
+} YvGemm;
+int yv_gemm(const YvGemm* g, yv_stream_t stream);
+
+/* fp32 -> bf16 plane pair (activations entering the path, e.g. the 2048-d region features) */
+int yv_split_planes(const float* src, int64_t ld_src, void* planes, int64_t ld_dst, int64_t plane_stride,
+                    int64_t rows, int64_t cols, yv_stream_t stream);
+/* all weights in one launch: seg table lives on the device */
+typedef struct {
+    const float* src;
+    int64_t dst_off;   /* element offset into the hi plane */
+    int64_t numel;
+    int64_t first_blk; /* prefix sum of ceil(numel / 2048) */
+} YvSplitSeg;
+int yv_split_multi(const YvSplitSeg* segs_dev, int32_t nseg, int64_t total_blocks, void* planes,
+                   int64_t plane_stride, yv_stream_t stream);
+
+/* dropout RNG state {seed, step}: step += 1 (captured once per training step) */
+int yv_rng_advance(uint64_t* rng, yv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (vilbert/vilbert.py:204-217: biased variance, eps inside the sqrt), optionally followed by
+ * dropout (embeddings: :254-255, :1367-1368).  y32 and/or y_planes may be NULL.  stats = {mean, rstd}[M].
+ * bwd: dx = LN'(dy) (+ dx_add), dgamma/dbeta accumulated with atomics into zero-initialised buffers.
+ *      dx_planes (optional) = dx * dropmask(pre_site): the operand of the preceding dense layer's
+ *      dgrad/wgrad when that layer's output went through dropout before the residual add (:323-324).
+ * ---------------------------------------------------------------------------------------------- */
+int yv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32,
+                     void* y_planes, int64_t plane_stride, float* stats, int64_t M, int32_t C, float drop_p,
+                     uint32_t drop_site, const uint64_t* rng, yv_stream_t stream);
+int yv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats,
+                     float post_drop_p, uint32_t post_drop_site, const float* dx_add, float* dx32,
+                     void* dx_planes, int64_t plane_stride, float pre_drop_p, uint32_t pre_drop_site,
+                     const uint64_t* rng, float* dgamma, float* dbeta, int64_t M, int32_t C, yv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * attention softmax (vilbert/vilbert.py:295-304, 424-433, 578-589, 598-611):
+ *   P = softmax(S * scale + mask[pair, key]); S is overwritten by P (kept for backward);
+ *   planes = dropout(P) split to bf16 hi/lo.   rows = pairs*heads*Tq, row r belongs to pair r / rows_per_pair.
+ * bwd: dS = scale * P * (dPd*m - sum_j P*dPd*m) with m the recomputed dropout multiplier -> planes.
+ * ---------------------------------------------------------------------------------------------- */
+int yv_softmax_fwd(float* s, int64_t ld_s, const float* mask, int64_t rows, int32_t cols, int64_t rows_per_pair,
+                   float scale, void* p_planes, int64_t ld_p, int64_t plane_stride, float drop_p,
+                   uint32_t drop_site, const uint64_t* rng, yv_stream_t stream);
+int yv_softmax_bwd(const float* p, const float* dpd, int64_t ld_s, int64_t rows, int32_t cols, float scale,
+                   void* ds_planes, int64_t ld_p, int64_t plane_stride, float drop_p, uint32_t drop_site,
+                   const uint64_t* rng, yv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * embeddings
+ *   text  (vilbert/vilbert.py:240-253): out[m] = word[tok[m]] + pos[m % T] + type[seg[m]]
+ *   image (vilbert/vilbert.py:1361-1365): out[m] = W5.loc[0:5]+b5 + W4.loc[5:9]+b4 + W2.loc[9:11]+b2 + seq[loc[11]]
+ *          (the 2048->1024 projection is a yv_gemm with this tensor as its residual)
+ * bwd scatters with atomics into zero-initialised (or accumulating) gradient buffers.
+ * ---------------------------------------------------------------------------------------------- */
+int yv_embed_text_fwd(const int64_t* tok, const int64_t* seg, const float* word, const float* pos,
+                      const float* type, float* out, int64_t M, int32_t T, int32_t H, yv_stream_t stream);
+int yv_embed_text_bwd(const int64_t* tok, const int64_t* seg, const float* dout, float* dword, float* dpos,
+                      float* dtype_, int64_t M, int32_t T, int32_t H, int32_t padding_idx, yv_stream_t stream);
+int yv_embed_loc_fwd(const float* loc, const float* w5, const float* b5, const float* w4, const float* b4,
+                     const float* w2, const float* b2, const float* seq, float* out, int64_t M, int32_t H,
+                     yv_stream_t stream);
+int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5, float* db5, float* dw4, float* db4,
+                     float* dw2, float* db2, float* dseq, int64_t M, int32_t H, yv_stream_t stream);
+
+/* column sums of an f32 matrix (bias gradients): out[c] (+)= sum_r x[r, c] */
+int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out, int32_t accumulate,
+              yv_stream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * fused losses (utils/utils_init.py:117-135)
+ *   ce : masked-language cross entropy, ignore_index = -1, mean over kept rows.
+ *        loss_sum[0] += sum_rows(-log p[target]); count[0] += kept rows;  dlogits planes (optional) get
+ *        (softmax - onehot) * grad_scale[0] / max(count,1) for kept rows, 0 otherwise (two-phase: call with
+ *        dl_planes == NULL first to obtain count, or pass count_in).
+ *   kl : masked-vision KL(target || softmax(logits)) summed over rows with mask, / max(1, sum(mask)).
+ * ---------------------------------------------------------------------------------------------- */
+int yv_ce_loss(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int32_t cols,
+               float* loss_sum, float* count, yv_stream_t stream);
+int yv_ce_grad(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int32_t cols,
+               const float* count, const float* gscale, float* dl32, void* dl_planes, int64_t ld_p,
+               int64_t plane_stride, yv_stream_t stream);
+int yv_kl_loss(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* mask,
+               int64_t rows, int32_t cols, float* loss_sum, float* count, yv_stream_t stream);
+int yv_kl_grad(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* mask,
+               int64_t rows, int32_t cols, const float* count, const float* gscale, float* dl32,
+               void* dl_planes, int64_t ld_p, int64_t plane_stride, yv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YVB200_H */

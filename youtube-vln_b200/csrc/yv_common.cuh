@@ -1,0 +1,95 @@
+// Shared device helpers for the yvb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define YV_DEVINL __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host): every C-ABI entry returns 0 / non-zero and leaves a message behind
+// ---------------------------------------------------------------------------------------------
+void yv_set_error(const char* fmt, ...);
+#define YV_CHECK(cond, ...)                \
+    do {                                   \
+        if (!(cond)) {                     \
+            yv_set_error(__VA_ARGS__);     \
+            return 1;                      \
+        }                                  \
+    } while (0)
+#define YV_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            yv_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                         __LINE__);                                                         \
+            return 2;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout RNG: stateless hash of (element index, site key, step key)
+//   rng[0] = seed, rng[1] = step counter (advanced by yv_rng_advance once per training step, so a
+//   captured CUDA graph draws fresh masks on every replay).  Backward recomputes the same mask.
+// ---------------------------------------------------------------------------------------------
+YV_DEVINL uint32_t yv_mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+struct YvDrop {
+    uint32_t k0, k1, thresh;
+    float scale;  // 1/(1-p); thresh == 0 -> dropout disabled
+};
+
+YV_DEVINL YvDrop yv_drop_make(const unsigned long long* rng, uint32_t site, float p) {
+    YvDrop d;
+    d.thresh = 0;
+    d.scale = 1.f;
+    d.k0 = d.k1 = 0;
+    if (p > 0.f && rng != nullptr) {
+        unsigned long long seed = rng[0], step = rng[1];
+        d.k0 = yv_mix32((uint32_t)seed ^ (site * 0x9E3779B1U));
+        d.k1 = yv_mix32((uint32_t)(seed >> 32) + (uint32_t)step * 0x85EBCA77U + (uint32_t)(step >> 32));
+        double t = (double)p * 4294967296.0;
+        d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFU : (uint32_t)t;
+        d.scale = 1.f / (1.f - p);
+    }
+    return d;
+}
+
+// multiplier applied to element `idx`: 0 (dropped) or 1/(1-p) (kept)
+YV_DEVINL float yv_drop_mul(const YvDrop& d, uint32_t idx) {
+    if (d.thresh == 0) return 1.f;
+    uint32_t h = yv_mix32(yv_mix32(idx ^ d.k0) + d.k1);
+    return h >= d.thresh ? d.scale : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// math
+// ---------------------------------------------------------------------------------------------
+YV_DEVINL float yv_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+YV_DEVINL float yv_gelu_grad(float x) {
+    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// split an fp32 value into a bf16 "hi" plane and a bf16 "lo" residual plane (x ~= hi + lo)
+YV_DEVINL void yv_split(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+YV_DEVINL float yv_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+YV_DEVINL float yv_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

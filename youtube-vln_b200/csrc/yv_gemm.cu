@@ -1,0 +1,434 @@
+// yv_gemm: batched, hi/lo-split (bf16x3) tcgen05 GEMM with a fused row-owning epilogue.  sm_100a only.
+//
+//   D[z] = epilogue(alpha * sum_p A_p[z] . B_p[z]^T)        p in {(hi,hi)} or {(hi,hi),(hi,lo),(lo,hi)}
+//
+// One CTA per 128x128 output tile, 192 threads:
+//   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d with 128B swizzle into a 3/6-stage ring
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), commits to mbarriers
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns, thread owns one output row
+// Operands may be K-major or MN-major (transposed views): dgrad / wgrad / attention products need no
+// explicit transposes.  Out-of-bounds rows/cols/k are zero-filled by TMA (each batch dim is its own
+// tensor-map dim), so ragged shapes (T=80, vocab 30522, 1601 classes) need no padding copies.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/yvb200.h"
+#include "yv_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int BLOCK_K = 64;                                   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 16 KB (A and B tiles have the same size)
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+template <int PASSES>
+struct Cfg {
+    static constexpr int TILES_PER_STAGE = PASSES == 3 ? 4 : 2;   // A_hi, B_hi, (A_lo, B_lo)
+    static constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
+    static constexpr int STAGES = PASSES == 3 ? 3 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct KParams {
+    int M, N, K;
+    int nb0;
+    int a_mn, b_mn;
+    float alpha;
+    int act;
+    const float* bias;
+    float* aux_out;
+    const float* aux_in;
+    const float* residual;
+    float* out32;
+    long long ld_out, out_sb0, out_sb1;
+    __nv_bfloat16* out_planes;
+    long long ld_pl, pl_sb0, pl_sb1, pl_plane_stride;
+    float drop_p;
+    unsigned drop_site;
+    const unsigned long long* rng;
+};
+
+// ------------------------------------------------------------------------------------------- PTX
+YV_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+YV_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+YV_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+YV_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a protocol bug must not hang the GPU
+    }
+}
+YV_DEVINL void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                           int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(dst),
+        "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+YV_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+YV_DEVINL void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+YV_DEVINL void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+        "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused
+//   MN-major: 64-element chunks along M/N are LBO bytes apart, 8-k-row groups 1024 B apart (SBO)
+YV_DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+template <int PASSES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const KParams p) {
+    using C = Cfg<PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + C::STAGES * C::STAGE_BYTES);
+    // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full; then the TMEM base address word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BLOCK_M;
+    const int n0 = blockIdx.x * BLOCK_N;
+    const int z = blockIdx.z;
+    const int b0 = z % p.nb0, b1 = z / p.nb0;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                const int k0 = kb * BLOCK_K;
+#pragma unroll
+                for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
+                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                    if (!p.a_mn) {
+                        tma_load_5d(sa, &map_a, full_bar(stage), k0, m0, b0, b1, pl);
+                    } else {
+                        tma_load_5d(sa, &map_a, full_bar(stage), m0, k0, b0, b1, pl);
+                        tma_load_5d(sa + TILE_BYTES / 2, &map_a, full_bar(stage), m0 + 64, k0, b0, b1, pl);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_5d(sb, &map_b, full_bar(stage), k0, n0, b0, b1, pl);
+                    } else {
+                        tma_load_5d(sb, &map_b, full_bar(stage), n0, k0, b0, b1, pl);
+                        tma_load_5d(sb + TILE_BYTES / 2, &map_b, full_bar(stage), n0 + 64, k0, b0, b1, pl);
+                    }
+                }
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ========================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
+                                   ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            // per-UMMA_K advance of the descriptor start address (in 16-byte units)
+            const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accum = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                uint64_t da[2], db[2];
+#pragma unroll
+                for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
+                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024) : make_desc(sa, 16, 1024);
+                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024) : make_desc(sb, 16, 1024);
+                }
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    if (PASSES == 3) {
+                        // small cross terms first, the dominant hi*hi term last
+                        umma_bf16(tmem_base, da[1] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                        accum = 1;
+                        umma_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[1] + (uint64_t)(b_step * k), idesc, 1);
+                    }
+                    umma_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                    accum = 1;
+                }
+                umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs retire
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(tmem_full_bar);          // accumulator complete -> epilogue
+        }
+    } else {
+        // ===================================== epilogue ==========================================
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
+        const bool row_ok = row < p.M;
+        const long long obase = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1 + (long long)row * p.ld_out;
+        const long long pbase = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1 + (long long)row * p.ld_pl;
+        const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.out_sb0 & 3) == 0) && ((p.out_sb1 & 3) == 0) &&
+                            ((p.ld_pl & 7) == 0) && ((p.pl_sb0 & 7) == 0) && ((p.pl_sb1 & 7) == 0) &&
+                            ((p.pl_plane_stride & 7) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            const int nc = n0 + c * 32;
+            if (nc >= p.N) break;                            // warp-uniform
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+            if (!row_ok) continue;
+            float v[32];
+            const bool full = (nc + 32 <= p.N) && vec_ok;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nc + j;
+                float x = p.alpha * __uint_as_float(raw[j]);
+                if (n < p.N) {
+                    if (p.bias) x += __ldg(p.bias + n);
+                    if (p.aux_out) p.aux_out[obase + n] = x;
+                    if (p.act == YV_ACT_GELU) x = yv_gelu(x);
+                    else if (p.act == YV_ACT_RELU) x = fmaxf(x, 0.f);
+                    if (drop.thresh)
+                        x *= yv_drop_mul(drop, (uint32_t)(((long long)z * p.M + row) * p.N + n));
+                    if (p.act == YV_ACT_MUL_GELU_GRAD) x *= yv_gelu_grad(p.aux_in[obase + n]);
+                    else if (p.act == YV_ACT_MUL_RELU_MASK) x = p.aux_in[obase + n] > 0.f ? x : 0.f;
+                    if (p.residual) x += p.residual[obase + n];
+                }
+                v[j] = x;
+            }
+            if (p.out32) {
+                if (full) {
+                    float4* o = reinterpret_cast<float4*>(p.out32 + obase + nc);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (nc + j < p.N) p.out32[obase + nc + j] = v[j];
+                }
+            }
+            if (p.out_planes) {
+                __nv_bfloat16* hi = p.out_planes + pbase + nc;
+                __nv_bfloat16* lo = hi + p.pl_plane_stride;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __align__(16) __nv_bfloat16 h8[8], l8[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) yv_split(v[8 * j + t], h8[t], l8[t]);
+                        reinterpret_cast<uint4*>(hi)[j] = *reinterpret_cast<uint4*>(h8);
+                        if (PASSES == 3) reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (nc + j < p.N) {
+                            __nv_bfloat16 h, l;
+                            yv_split(v[j], h, l);
+                            hi[j] = h;
+                            if (PASSES == 3) lo[j] = l;
+                        }
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+        yv_set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return 0;
+}
+
+int make_map(CUtensorMap* map, const YvOperand& o, int passes, const char* which) {
+    YV_CHECK(o.ptr != nullptr, "yv_gemm: operand %s is NULL", which);
+    YV_CHECK(((uintptr_t)o.ptr & 15) == 0, "yv_gemm: operand %s not 16-byte aligned", which);
+    YV_CHECK(o.inner > 0 && o.rows > 0 && o.nb0 > 0 && o.nb1 > 0, "yv_gemm: operand %s has empty extent", which);
+    YV_CHECK((o.ld & 7) == 0 && o.ld >= o.inner, "yv_gemm: operand %s ld=%lld must be a multiple of 8 and >= inner=%lld",
+             which, (long long)o.ld, (long long)o.inner);
+    YV_CHECK((o.nb0 == 1 || (o.sb0 & 7) == 0) && (o.nb1 == 1 || (o.sb1 & 7) == 0),
+             "yv_gemm: operand %s batch strides must be multiples of 8 elements", which);
+    YV_CHECK(passes == 1 || ((o.plane_stride & 7) == 0 && o.plane_stride > 0),
+             "yv_gemm: operand %s plane_stride must be a positive multiple of 8", which);
+    const int nplanes = passes == 3 ? 2 : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)o.inner, (cuuint64_t)o.rows, (cuuint64_t)o.nb0, (cuuint64_t)o.nb1,
+                          (cuuint64_t)nplanes};
+    // strides of dims 1..4 in bytes (dim 0 is contiguous); unused dims get a harmless valid stride
+    const cuuint64_t row_b = (cuuint64_t)o.ld * 2;
+    cuuint64_t strides[4] = {row_b, o.nb0 > 1 ? (cuuint64_t)o.sb0 * 2 : row_b, o.nb1 > 1 ? (cuuint64_t)o.sb1 * 2 : row_b,
+                             nplanes > 1 ? (cuuint64_t)o.plane_stride * 2 : row_b};
+    cuuint32_t box[5] = {64, (cuuint32_t)(o.mn_major ? BLOCK_K : BLOCK_M), 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(o.ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YV_CHECK(r == CUDA_SUCCESS, "yv_gemm: cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", which,
+             (int)r, (long long)o.inner, (long long)o.rows, (long long)o.ld);
+    return 0;
+}
+
+}  // namespace
+
+void yv_count_launch();
+
+extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
+    YV_CHECK(g != nullptr, "yv_gemm: NULL args");
+    YV_CHECK(g->passes == 1 || g->passes == 3, "yv_gemm: passes must be 1 or 3 (got %d)", g->passes);
+    YV_CHECK(g->M > 0 && g->N > 0 && g->K > 0, "yv_gemm: empty problem M=%d N=%d K=%d", g->M, g->N, g->K);
+    YV_CHECK(g->out32 || g->out_planes, "yv_gemm: no output requested");
+    if (get_encode()) return 1;
+    // operand extents must agree with the problem
+    const YvOperand &a = g->a, &b = g->b;
+    YV_CHECK((a.mn_major ? a.inner : a.rows) == g->M && (a.mn_major ? a.rows : a.inner) == g->K,
+             "yv_gemm: A extents (%lld x %lld, mn_major=%d) do not match M=%d K=%d", (long long)a.rows, (long long)a.inner,
+             a.mn_major, g->M, g->K);
+    YV_CHECK((b.mn_major ? b.inner : b.rows) == g->N && (b.mn_major ? b.rows : b.inner) == g->K,
+             "yv_gemm: B extents (%lld x %lld, mn_major=%d) do not match N=%d K=%d", (long long)b.rows, (long long)b.inner,
+             b.mn_major, g->N, g->K);
+    YV_CHECK(a.nb0 == b.nb0 && a.nb1 == b.nb1, "yv_gemm: batch counts differ");
+    CUtensorMap ma, mb;
+    if (make_map(&ma, a, g->passes, "A")) return 1;
+    if (make_map(&mb, b, g->passes, "B")) return 1;
+
+    KParams p;
+    p.M = g->M; p.N = g->N; p.K = g->K;
+    p.nb0 = (int)a.nb0;
+    p.a_mn = a.mn_major ? 1 : 0;
+    p.b_mn = b.mn_major ? 1 : 0;
+    p.alpha = g->alpha;
+    p.act = g->act;
+    p.bias = g->bias;
+    p.aux_out = g->aux_out;
+    p.aux_in = g->aux_in;
+    p.residual = g->residual;
+    p.out32 = g->out32;
+    p.ld_out = g->ld_out; p.out_sb0 = g->out_sb0; p.out_sb1 = g->out_sb1;
+    p.out_planes = reinterpret_cast<__nv_bfloat16*>(g->out_planes);
+    p.ld_pl = g->ld_pl; p.pl_sb0 = g->pl_sb0; p.pl_sb1 = g->pl_sb1; p.pl_plane_stride = g->pl_plane_stride;
+    p.drop_p = g->drop_p; p.drop_site = g->drop_site;
+    p.rng = reinterpret_cast<const unsigned long long*>(g->rng);
+    YV_CHECK((g->act != YV_ACT_MUL_GELU_GRAD && g->act != YV_ACT_MUL_RELU_MASK) || g->aux_in,
+             "yv_gemm: act %d needs aux_in", g->act);
+
+    dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, (unsigned)(a.nb0 * a.nb1));
+    YV_CHECK(grid.y <= 65535 && grid.z <= 65535, "yv_gemm: grid too large");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    static bool attr_set = false;
+    if (!attr_set) {
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
+        attr_set = true;
+    }
+    if (g->passes == 3)
+        yv_gemm_kernel<3><<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, st>>>(ma, mb, p);
+    else
+        yv_gemm_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(ma, mb, p);
+    YV_CUDA(cudaGetLastError());
+    yv_count_launch();
+    return 0;
+}

@@ -1,0 +1,647 @@
+// Row-wise / elementwise kernels of the ViLBERT hot path (HBM/L2-bound work; no tensor cores).
+// One warp per row for LayerNorm / softmax (rows are 64..1152 floats), coalesced lane-strided columns.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/yvb200.h"
+#include "yv_common.cuh"
+
+void yv_count_launch();
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 hi/lo planes
+// ------------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                    long long ld_dst, long long plane_stride, long long rows, long long cols) {
+    const long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        __nv_bfloat16 h, l;
+        yv_split(src[r * ld_src + c], h, l);
+        dst[r * ld_dst + c] = h;
+        dst[plane_stride + r * ld_dst + c] = l;
+    }
+}
+
+constexpr int SPLIT_BLK = 2048;  // elements per block in the multi-tensor kernel
+__global__ void split_multi_kernel(const YvSplitSeg* __restrict__ segs, int nseg, __nv_bfloat16* __restrict__ planes,
+                                   long long plane_stride) {
+    const long long blk = blockIdx.x;
+    int lo = 0, hi = nseg - 1;                       // last segment with first_blk <= blk
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].first_blk <= blk) lo = mid; else hi = mid - 1;
+    }
+    const YvSplitSeg s = segs[lo];
+    const long long base = (blk - s.first_blk) * SPLIT_BLK;
+    const float* src = s.src + base;
+    __nv_bfloat16* dh = planes + s.dst_off + base;
+    __nv_bfloat16* dl = dh + plane_stride;
+    const long long n = min((long long)SPLIT_BLK, s.numel - base);
+    const bool vec = ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dh) & 7) == 0) && ((plane_stride & 3) == 0);
+    if (vec && n == SPLIT_BLK) {
+        for (int i = threadIdx.x; i < SPLIT_BLK / 4; i += blockDim.x) {
+            const float4 v = reinterpret_cast<const float4*>(src)[i];
+            __align__(8) __nv_bfloat16 h[4], l[4];
+            yv_split(v.x, h[0], l[0]); yv_split(v.y, h[1], l[1]); yv_split(v.z, h[2], l[2]); yv_split(v.w, h[3], l[3]);
+            reinterpret_cast<uint2*>(dh)[i] = *reinterpret_cast<uint2*>(h);
+            reinterpret_cast<uint2*>(dl)[i] = *reinterpret_cast<uint2*>(l);
+        }
+    } else {
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            __nv_bfloat16 h, l;
+            yv_split(src[i], h, l);
+            dh[i] = h;
+            dl[i] = l;
+        }
+    }
+}
+
+__global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1ULL; }
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yp, long long plane_stride,
+                     float* __restrict__ stats, long long M, int C, float drop_p, unsigned drop_site,
+                     const unsigned long long* rng) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* xr = x + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = yv_warp_sum(s) / C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float d = xr[c] - mean;
+        v += d * d;
+    }
+    const float var = yv_warp_sum(v) / C;
+    const float rstd = 1.f / sqrtf(var + eps);
+    if (stats && lane == 0) {
+        stats[2 * row] = mean;
+        stats[2 * row + 1] = rstd;
+    }
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+    for (int c = lane; c < C; c += 32) {
+        float y = gamma[c] * ((xr[c] - mean) * rstd) + beta[c];
+        if (drop.thresh) y *= yv_drop_mul(drop, (uint32_t)(row * C + c));
+        if (y32) y32[row * C + c] = y;
+        if (yp) {
+            __nv_bfloat16 h, l;
+            yv_split(y, h, l);
+            yp[row * C + c] = h;
+            yp[plane_stride + row * C + c] = l;
+        }
+    }
+}
+
+// grid-stride over rows; per-lane register accumulators for dgamma/dbeta (C <= 32*MAXPL)
+template <int MAXPL>
+__global__ void __launch_bounds__(THREADS)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ stats, float post_p, unsigned post_site, const float* __restrict__ dx_add,
+                     float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxp, long long plane_stride, float pre_p,
+                     unsigned pre_site, const unsigned long long* rng, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, long long M, int C) {
+    __shared__ float red[WARPS][32 * MAXPL + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const YvDrop dpost = yv_drop_make(rng, post_site, post_p);
+    const YvDrop dpre = yv_drop_make(rng, pre_site, pre_p);
+    float ag[MAXPL], ab[MAXPL];
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) ag[i] = ab[i] = 0.f;
+    for (long long row = blockIdx.x * (long long)WARPS + warp; row < M; row += (long long)gridDim.x * WARPS) {
+        const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+        const float* xr = x + row * C;
+        const float* dyr = dy + row * C;
+        float g[MAXPL], xh[MAXPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXPL; ++i) {
+            const int c = lane + 32 * i;
+            g[i] = 0.f; xh[i] = 0.f;
+            if (c < C) {
+                float d = dyr[c];
+                if (dpost.thresh) d *= yv_drop_mul(dpost, (uint32_t)(row * C + c));
+                xh[i] = (xr[c] - mean) * rstd;
+                ag[i] += d * xh[i];
+                ab[i] += d;
+                g[i] = d * gamma[c];
+                s1 += g[i];
+                s2 += g[i] * xh[i];
+            }
+        }
+        s1 = yv_warp_sum(s1) / C;
+        s2 = yv_warp_sum(s2) / C;
+#pragma unroll
+        for (int i = 0; i < MAXPL; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+                float d = rstd * (g[i] - s1 - xh[i] * s2);
+                if (dx_add) d += dx_add[row * C + c];
+                if (dx32) dx32[row * C + c] = d;
+                if (dxp) {
+                    float dd = d;
+                    if (dpre.thresh) dd *= yv_drop_mul(dpre, (uint32_t)(row * C + c));
+                    __nv_bfloat16 h, l;
+                    yv_split(dd, h, l);
+                    dxp[row * C + c] = h;
+                    dxp[plane_stride + row * C + c] = l;
+                }
+            }
+        }
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;
+    // block reduction of the per-warp partial sums, then one atomic per column per block
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int i = 0; i < MAXPL; ++i) red[warp][lane + 32 * i] = pass == 0 ? ag[i] : ab[i];
+        __syncthreads();
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst)
+            for (int c = threadIdx.x; c < C; c += THREADS) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) t += red[w][c];
+                atomicAdd(dst + c, t);
+            }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention softmax
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+softmax_fwd_kernel(float* __restrict__ s, long long ld_s, const float* __restrict__ mask, long long rows, int cols,
+                   long long rows_per_pair, float scale, __nv_bfloat16* __restrict__ pp, long long ld_p,
+                   long long plane_stride, float drop_p, unsigned drop_site, const unsigned long long* rng) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* sr = s + row * ld_s;
+    const float* mr = mask ? mask + (row / rows_per_pair) * cols : nullptr;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) {
+        const float v = sr[c] * scale + (mr ? mr[c] : 0.f);
+        sr[c] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = yv_warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+        const float e = expf(sr[c] - mx);
+        sr[c] = e;
+        sum += e;
+    }
+    sum = yv_warp_sum(sum);
+    const float inv = 1.f / sum;
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+    for (int c = lane; c < cols; c += 32) {
+        const float pr = sr[c] * inv;
+        sr[c] = pr;
+        float pd = pr;
+        if (drop.thresh) pd *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
+        __nv_bfloat16 h, l;
+        yv_split(pd, h, l);
+        pp[row * ld_p + c] = h;
+        pp[plane_stride + row * ld_p + c] = l;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd, long long ld_s, long long rows, int cols,
+                   float scale, __nv_bfloat16* __restrict__ dsp, long long ld_p, long long plane_stride, float drop_p,
+                   unsigned drop_site, const unsigned long long* rng) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* pr = p + row * ld_s;
+    const float* dr = dpd + row * ld_s;
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+        float d = dr[c];
+        if (drop.thresh) d *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
+        dot += d * pr[c];
+    }
+    dot = yv_warp_sum(dot);
+    for (int c = lane; c < cols; c += 32) {
+        float d = dr[c];
+        if (drop.thresh) d *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
+        const float ds = scale * pr[c] * (d - dot);
+        __nv_bfloat16 h, l;
+        yv_split(ds, h, l);
+        dsp[row * ld_p + c] = h;
+        dsp[plane_stride + row * ld_p + c] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embeddings
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_text_fwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ seg,
+                                      const float* __restrict__ word, const float* __restrict__ pos,
+                                      const float* __restrict__ type, float* __restrict__ out, long long M, int T, int H) {
+    const long long m = blockIdx.x;
+    const float* w = word + tok[m] * (long long)H;
+    const float* ps = pos + (m % T) * (long long)H;
+    const float* ty = type + seg[m] * (long long)H;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) out[m * H + h] = w[h] + ps[h] + ty[h];
+}
+
+__global__ void embed_text_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ seg,
+                                      const float* __restrict__ dout, float* __restrict__ dword, float* __restrict__ dpos,
+                                      float* __restrict__ dtype_, long long M, int T, int H, int padding_idx) {
+    const long long m = blockIdx.x;
+    const long long t = tok[m];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        const float g = dout[m * H + h];
+        if (dword && t != padding_idx) atomicAdd(dword + t * H + h, g);
+        if (dpos) atomicAdd(dpos + (m % T) * (long long)H + h, g);
+        if (dtype_) atomicAdd(dtype_ + seg[m] * (long long)H + h, g);
+    }
+}
+
+__global__ void embed_loc_fwd_kernel(const float* __restrict__ loc, const float* __restrict__ w5, const float* __restrict__ b5,
+                                     const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ w2,
+                                     const float* __restrict__ b2, const float* __restrict__ seq, float* __restrict__ out,
+                                     long long M, int H) {
+    const long long m = blockIdx.x;
+    __shared__ float l[12];
+    if (threadIdx.x < 12) l[threadIdx.x] = loc[m * 12 + threadIdx.x];
+    __syncthreads();
+    const long long sidx = (long long)l[11];
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        // same association order as the reference: ((a + b) + c) + d with a,b,c = W.x + bias
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) a += w5[h * 5 + j] * l[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b += w4[h * 4 + j] * l[5 + j];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) c += w2[h * 2 + j] * l[9 + j];
+        out[m * H + h] = (((a + b5[h]) + (b + b4[h])) + (c + b2[h])) + seq[sidx * H + h];
+    }
+}
+
+constexpr int LOC_ROWS = 32;
+__global__ void embed_loc_bwd_kernel(const float* __restrict__ loc, const float* __restrict__ dout, float* __restrict__ dw5,
+                                     float* __restrict__ db5, float* __restrict__ dw4, float* __restrict__ db4,
+                                     float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dseq, long long M,
+                                     int H) {
+    __shared__ float l[LOC_ROWS][12];
+    const long long r0 = blockIdx.x * (long long)LOC_ROWS;
+    const int nr = (int)min((long long)LOC_ROWS, M - r0);
+    for (int i = threadIdx.x; i < nr * 12; i += blockDim.x) l[i / 12][i % 12] = loc[r0 * 12 + i];
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float acc[11];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) acc[j] = 0.f;
+        float accb = 0.f;
+        for (int r = 0; r < nr; ++r) {
+            const float g = dout[(r0 + r) * H + h];
+            accb += g;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) acc[j] += g * l[r][j];
+            atomicAdd(dseq + (long long)l[r][11] * H + h, g);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) atomicAdd(dw5 + h * 5 + j, acc[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dw4 + h * 4 + j, acc[5 + j]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) atomicAdd(dw2 + h * 2 + j, acc[9 + j]);
+        atomicAdd(db5 + h, accb);
+        atomicAdd(db4 + h, accb);
+        atomicAdd(db2 + h, accb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients)
+// ------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 64;
+__global__ void colsum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = blockIdx.y * (long long)CS_ROWS;
+    const long long r1 = min(rows, r0 + CS_ROWS);
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += x[r * ld + c];
+    atomicAdd(out + c, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses: one block per row
+// ------------------------------------------------------------------------------------------------
+__device__ float block_max(float v, float* sh) {
+    v = yv_warp_max(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = -INFINITY;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+    __syncthreads();
+    return r;
+}
+__device__ float block_sum(float v, float* sh) {
+    v = yv_warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += sh[w];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(THREADS)
+ce_loss_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ target, int cols,
+               float* __restrict__ loss_sum, float* __restrict__ count) {
+    __shared__ float sh[WARPS];
+    const long long row = blockIdx.x;
+    const long long t = target[row];
+    if (t < 0) return;
+    const float* lr = logits + row * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += THREADS) mx = fmaxf(mx, lr[c]);
+    mx = block_max(mx, sh);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += THREADS) s += expf(lr[c] - mx);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(loss_sum, (mx + logf(s)) - lr[t]);
+        atomicAdd(count, 1.f);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+ce_grad_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ target, int cols,
+               const float* __restrict__ count, const float* __restrict__ gscale, float* __restrict__ dl32,
+               __nv_bfloat16* __restrict__ dlp, long long ld_p, long long plane_stride) {
+    __shared__ float sh[WARPS];
+    const long long row = blockIdx.x;
+    const long long t = target[row];
+    const float* lr = logits + row * ld;
+    float mx = 0.f, inv = 0.f, g = 0.f;
+    if (t >= 0) {
+        mx = -INFINITY;
+        for (int c = threadIdx.x; c < cols; c += THREADS) mx = fmaxf(mx, lr[c]);
+        mx = block_max(mx, sh);
+        float s = 0.f;
+        for (int c = threadIdx.x; c < cols; c += THREADS) s += expf(lr[c] - mx);
+        s = block_sum(s, sh);
+        inv = 1.f / s;
+        g = (gscale ? gscale[0] : 1.f) / fmaxf(count[0], 1.f);
+    }
+    for (int c = threadIdx.x; c < cols; c += THREADS) {
+        float d = 0.f;
+        if (t >= 0) d = g * (expf(lr[c] - mx) * inv - (c == t ? 1.f : 0.f));
+        if (dl32) dl32[row * ld + c] = d;
+        if (dlp) {
+            __nv_bfloat16 h, l;
+            yv_split(d, h, l);
+            dlp[row * ld_p + c] = h;
+            dlp[plane_stride + row * ld_p + c] = l;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+kl_loss_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, long long ld_t,
+               const long long* __restrict__ mask, int cols, float* __restrict__ loss_sum, float* __restrict__ count) {
+    __shared__ float sh[WARPS];
+    const long long row = blockIdx.x;
+    if (mask[row] == 0) return;
+    const float* lr = logits + row * ld;
+    const float* tr = target + row * ld_t;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += THREADS) mx = fmaxf(mx, lr[c]);
+    mx = block_max(mx, sh);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += THREADS) s += expf(lr[c] - mx);
+    s = block_sum(s, sh);
+    const float lse = mx + logf(s);
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < cols; c += THREADS) {
+        const float t = tr[c];
+        if (t > 0.f) acc += t * (logf(t) - (lr[c] - lse));
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(loss_sum, acc * (float)mask[row]);
+        atomicAdd(count, (float)mask[row]);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+kl_grad_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, long long ld_t,
+               const long long* __restrict__ mask, int cols, const float* __restrict__ count,
+               const float* __restrict__ gscale, float* __restrict__ dl32, __nv_bfloat16* __restrict__ dlp, long long ld_p,
+               long long plane_stride) {
+    __shared__ float sh[WARPS];
+    const long long row = blockIdx.x;
+    const float mk = (float)mask[row];
+    const float* lr = logits + row * ld;
+    const float* tr = target + row * ld_t;
+    float mx = 0.f, inv = 0.f, g = 0.f, tsum = 0.f;
+    if (mk != 0.f) {
+        mx = -INFINITY;
+        for (int c = threadIdx.x; c < cols; c += THREADS) mx = fmaxf(mx, lr[c]);
+        mx = block_max(mx, sh);
+        float s = 0.f, ts = 0.f;
+        for (int c = threadIdx.x; c < cols; c += THREADS) {
+            s += expf(lr[c] - mx);
+            ts += tr[c];
+        }
+        s = block_sum(s, sh);
+        tsum = block_sum(ts, sh);
+        inv = 1.f / s;
+        g = mk * (gscale ? gscale[0] : 1.f) / fmaxf(count[0], 1.f);
+    }
+    for (int c = threadIdx.x; c < cols; c += THREADS) {
+        float d = 0.f;
+        if (mk != 0.f) d = g * (expf(lr[c] - mx) * inv * tsum - tr[c]);
+        if (dl32) dl32[row * ld + c] = d;
+        if (dlp) {
+            __nv_bfloat16 h, l;
+            yv_split(d, h, l);
+            dlp[row * ld_p + c] = h;
+            dlp[plane_stride + row * ld_p + c] = l;
+        }
+    }
+}
+
+inline cudaStream_t S(yv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int grid_for(long long n, int per_block, int cap = 148 * 16) {
+    long long g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+}  // namespace
+
+#define YV_LAUNCHED()           \
+    YV_CUDA(cudaGetLastError()); \
+    yv_count_launch();           \
+    return 0
+
+extern "C" int yv_split_planes(const float* src, int64_t ld_src, void* planes, int64_t ld_dst, int64_t plane_stride,
+                               int64_t rows, int64_t cols, yv_stream_t stream) {
+    YV_CHECK(src && planes && rows > 0 && cols > 0, "yv_split_planes: bad arguments");
+    split_planes_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, S(stream)>>>(
+        src, ld_src, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst, plane_stride, rows, cols);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_split_multi(const YvSplitSeg* segs_dev, int32_t nseg, int64_t total_blocks, void* planes,
+                              int64_t plane_stride, yv_stream_t stream) {
+    YV_CHECK(segs_dev && planes && nseg > 0 && total_blocks > 0, "yv_split_multi: bad arguments");
+    YV_CHECK(total_blocks < 2147483647LL, "yv_split_multi: too many blocks");
+    split_multi_kernel<<<(unsigned)total_blocks, 256, 0, S(stream)>>>(segs_dev, nseg,
+                                                                      reinterpret_cast<__nv_bfloat16*>(planes), plane_stride);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_rng_advance(uint64_t* rng, yv_stream_t stream) {
+    YV_CHECK(rng, "yv_rng_advance: NULL state");
+    rng_advance_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned long long*>(rng));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32, void* y_planes,
+                                int64_t plane_stride, float* stats, int64_t M, int32_t C, float drop_p, uint32_t drop_site,
+                                const uint64_t* rng, yv_stream_t stream) {
+    YV_CHECK(x && gamma && beta && M > 0 && C > 0 && (y32 || y_planes), "yv_layernorm_fwd: bad arguments");
+    layernorm_fwd_kernel<<<(unsigned)((M + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
+        x, gamma, beta, eps, y32, reinterpret_cast<__nv_bfloat16*>(y_planes), plane_stride, stats, M, C, drop_p, drop_site,
+        reinterpret_cast<const unsigned long long*>(rng));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, float post_drop_p,
+                                uint32_t post_drop_site, const float* dx_add, float* dx32, void* dx_planes,
+                                int64_t plane_stride, float pre_drop_p, uint32_t pre_drop_site, const uint64_t* rng,
+                                float* dgamma, float* dbeta, int64_t M, int32_t C, yv_stream_t stream) {
+    YV_CHECK(dy && x && gamma && stats && M > 0 && C > 0, "yv_layernorm_bwd: bad arguments");
+    YV_CHECK(C <= 1024, "yv_layernorm_bwd: hidden size %d > 1024 not supported", C);
+    const int grid = grid_for(M, WARPS, 148 * 2);
+    auto* rp = reinterpret_cast<const unsigned long long*>(rng);
+    auto* pl = reinterpret_cast<__nv_bfloat16*>(dx_planes);
+    if (C <= 128)
+        layernorm_bwd_kernel<4><<<grid, THREADS, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
+                                                                 pl, plane_stride, pre_drop_p, pre_drop_site, rp, dgamma, dbeta, M, C);
+    else
+        layernorm_bwd_kernel<32><<<grid, THREADS, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
+                                                                  pl, plane_stride, pre_drop_p, pre_drop_site, rp, dgamma, dbeta, M, C);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_softmax_fwd(float* s, int64_t ld_s, const float* mask, int64_t rows, int32_t cols, int64_t rows_per_pair,
+                              float scale, void* p_planes, int64_t ld_p, int64_t plane_stride, float drop_p,
+                              uint32_t drop_site, const uint64_t* rng, yv_stream_t stream) {
+    YV_CHECK(s && p_planes && rows > 0 && cols > 0 && rows_per_pair > 0, "yv_softmax_fwd: bad arguments");
+    softmax_fwd_kernel<<<(unsigned)((rows + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
+        s, ld_s, mask, rows, cols, rows_per_pair, scale, reinterpret_cast<__nv_bfloat16*>(p_planes), ld_p, plane_stride, drop_p,
+        drop_site, reinterpret_cast<const unsigned long long*>(rng));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_softmax_bwd(const float* p, const float* dpd, int64_t ld_s, int64_t rows, int32_t cols, float scale,
+                              void* ds_planes, int64_t ld_p, int64_t plane_stride, float drop_p, uint32_t drop_site,
+                              const uint64_t* rng, yv_stream_t stream) {
+    YV_CHECK(p && dpd && ds_planes && rows > 0 && cols > 0, "yv_softmax_bwd: bad arguments");
+    softmax_bwd_kernel<<<(unsigned)((rows + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
+        p, dpd, ld_s, rows, cols, scale, reinterpret_cast<__nv_bfloat16*>(ds_planes), ld_p, plane_stride, drop_p, drop_site,
+        reinterpret_cast<const unsigned long long*>(rng));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_embed_text_fwd(const int64_t* tok, const int64_t* seg, const float* word, const float* pos,
+                                 const float* type, float* out, int64_t M, int32_t T, int32_t H, yv_stream_t stream) {
+    YV_CHECK(tok && seg && word && pos && type && out && M > 0, "yv_embed_text_fwd: bad arguments");
+    embed_text_fwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(tok),
+                                                              reinterpret_cast<const long long*>(seg), word, pos, type, out, M, T, H);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_embed_text_bwd(const int64_t* tok, const int64_t* seg, const float* dout, float* dword, float* dpos,
+                                 float* dtype_, int64_t M, int32_t T, int32_t H, int32_t padding_idx, yv_stream_t stream) {
+    YV_CHECK(tok && seg && dout && M > 0, "yv_embed_text_bwd: bad arguments");
+    embed_text_bwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(tok),
+                                                              reinterpret_cast<const long long*>(seg), dout, dword, dpos, dtype_, M,
+                                                              T, H, padding_idx);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_embed_loc_fwd(const float* loc, const float* w5, const float* b5, const float* w4, const float* b4,
+                                const float* w2, const float* b2, const float* seq, float* out, int64_t M, int32_t H,
+                                yv_stream_t stream) {
+    YV_CHECK(loc && w5 && b5 && w4 && b4 && w2 && b2 && seq && out && M > 0, "yv_embed_loc_fwd: bad arguments");
+    embed_loc_fwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(loc, w5, b5, w4, b4, w2, b2, seq, out, M, H);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5, float* db5, float* dw4, float* db4, float* dw2,
+                                float* db2, float* dseq, int64_t M, int32_t H, yv_stream_t stream) {
+    YV_CHECK(loc && dout && dw5 && db5 && dw4 && db4 && dw2 && db2 && dseq && M > 0, "yv_embed_loc_bwd: bad arguments");
+    embed_loc_bwd_kernel<<<(unsigned)((M + LOC_ROWS - 1) / LOC_ROWS), 256, 0, S(stream)>>>(loc, dout, dw5, db5, dw4, db4, dw2,
+                                                                                          db2, dseq, M, H);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out, int32_t accumulate,
+                         yv_stream_t stream) {
+    YV_CHECK(x && out && rows > 0 && cols > 0, "yv_colsum: bad arguments");
+    if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
+    dim3 grid((cols + 127) / 128, (unsigned)((rows + CS_ROWS - 1) / CS_ROWS));
+    colsum_kernel<<<grid, 128, 0, S(stream)>>>(x, ld, rows, cols, out);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_ce_loss(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int32_t cols, float* loss_sum,
+                          float* count, yv_stream_t stream) {
+    YV_CHECK(logits && target && loss_sum && count && rows > 0 && cols > 0, "yv_ce_loss: bad arguments");
+    ce_loss_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target), cols,
+                                                             loss_sum, count);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_ce_grad(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int32_t cols, const float* count,
+                          const float* gscale, float* dl32, void* dl_planes, int64_t ld_p, int64_t plane_stride,
+                          yv_stream_t stream) {
+    YV_CHECK(logits && target && count && (dl32 || dl_planes) && rows > 0 && cols > 0, "yv_ce_grad: bad arguments");
+    ce_grad_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target), cols, count,
+                                                             gscale, dl32, reinterpret_cast<__nv_bfloat16*>(dl_planes), ld_p,
+                                                             plane_stride);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_kl_loss(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* mask, int64_t rows,
+                          int32_t cols, float* loss_sum, float* count, yv_stream_t stream) {
+    YV_CHECK(logits && target && mask && loss_sum && count && rows > 0 && cols > 0, "yv_kl_loss: bad arguments");
+    kl_loss_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
+                                                             cols, loss_sum, count);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_kl_grad(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* mask, int64_t rows,
+                          int32_t cols, const float* count, const float* gscale, float* dl32, void* dl_planes, int64_t ld_p,
+                          int64_t plane_stride, yv_stream_t stream) {
+    YV_CHECK(logits && target && mask && count && (dl32 || dl_planes) && rows > 0 && cols > 0, "yv_kl_grad: bad arguments");
+    kl_grad_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
+                                                             cols, count, gscale, dl32, reinterpret_cast<__nv_bfloat16*>(dl_planes),
+                                                             ld_p, plane_stride);
+    YV_LAUNCHED();
+}
