@@ -133,6 +133,13 @@ int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5, float* db5
 /* column sums of an f32 matrix (bias gradients): out[c] (+)= sum_r x[r, c] */
 int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out, int32_t accumulate,
               yv_stream_t stream);
+int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_stride, int64_t rows, int32_t cols,
+                     float* out, int32_t accumulate, yv_stream_t stream);
+/* backward of the GEMM-epilogue activations when the upstream gradient arrives as f32:
+ * planes = dy * act'(aux)  (GELU: aux = saved pre-activation, vilbert/vilbert.py:113-119; ReLU: aux = output) */
+int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux, int64_t ld_aux, int32_t act, void* planes,
+                     int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, yv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * fused losses (utils/utils_init.py:117-135)
  *   ce : masked-language cross entropy, ignore_index = -1, mean over kept rows.

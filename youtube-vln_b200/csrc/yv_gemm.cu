@@ -306,7 +306,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int t = 0; t < 8; ++t) yv_split(v[8 * j + t], h8[t], l8[t]);
                         reinterpret_cast<uint4*>(hi)[j] = *reinterpret_cast<uint4*>(h8);
-                        if (PASSES == 3) reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
+                        reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
                     }
                 } else {
                     for (int j = 0; j < 32; ++j)
@@ -314,7 +314,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             __nv_bfloat16 h, l;
                             yv_split(v[j], h, l);
                             hi[j] = h;
-                            if (PASSES == 3) lo[j] = l;
+                            lo[j] = l;
                         }
                 }
             }

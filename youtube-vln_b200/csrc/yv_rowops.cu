@@ -343,6 +343,37 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, long lo
     atomicAdd(out + c, s);
 }
 
+// planes variant: x = hi + lo
+__global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long plane_stride, long long rows,
+                                     int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = blockIdx.y * (long long)CS_ROWS;
+    const long long r1 = min(rows, r0 + CS_ROWS);
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r)
+        s += __bfloat162float(x[r * ld + c]) + __bfloat162float(x[plane_stride + r * ld + c]);
+    atomicAdd(out + c, s);
+}
+
+// dpre = dy * act'(aux) -> planes   (GELU: aux = pre-activation; ReLU: aux = forward output)
+__global__ void act_bwd_split_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ aux,
+                                     long long ld_aux, int act, __nv_bfloat16* __restrict__ dst, long long ld_dst,
+                                     long long plane_stride, long long rows, long long cols) {
+    const long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        float d = dy[r * ld_dy + c];
+        if (act == YV_ACT_GELU) d *= yv_gelu_grad(aux[r * ld_aux + c]);
+        else if (act == YV_ACT_RELU) d = aux[r * ld_aux + c] > 0.f ? d : 0.f;
+        __nv_bfloat16 h, l;
+        yv_split(d, h, l);
+        dst[r * ld_dst + c] = h;
+        dst[plane_stride + r * ld_dst + c] = l;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // losses: one block per row
 // ------------------------------------------------------------------------------------------------
@@ -607,6 +638,25 @@ extern "C" int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols,
     if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
     dim3 grid((cols + 127) / 128, (unsigned)((rows + CS_ROWS - 1) / CS_ROWS));
     colsum_kernel<<<grid, 128, 0, S(stream)>>>(x, ld, rows, cols, out);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_stride, int64_t rows, int32_t cols, float* out,
+                                int32_t accumulate, yv_stream_t stream) {
+    YV_CHECK(planes && out && rows > 0 && cols > 0, "yv_colsum_planes: bad arguments");
+    if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
+    dim3 grid((cols + 127) / 128, (unsigned)((rows + CS_ROWS - 1) / CS_ROWS));
+    colsum_planes_kernel<<<grid, 128, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(planes), ld, plane_stride, rows,
+                                                      cols, out);
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux, int64_t ld_aux, int32_t act, void* planes,
+                                int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, yv_stream_t stream) {
+    YV_CHECK(dy && planes && rows > 0 && cols > 0, "yv_act_bwd_split: bad arguments");
+    YV_CHECK(act == YV_ACT_NONE || aux, "yv_act_bwd_split: act %d needs aux", act);
+    act_bwd_split_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, S(stream)>>>(
+        dy, ld_dy, aux, ld_aux, act, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst, plane_stride, rows, cols);
     YV_LAUNCHED();
 }
 

@@ -22,7 +22,7 @@ SYMBOLS = [
     "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_split_planes", "yv_split_multi",
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
-    "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
+    "yv_colsum_planes", "yv_act_bwd_split", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
 ]
 
 
@@ -93,27 +93,28 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class Planes:
-    """A bf16 hi/lo plane pair ``[2, rows, ld]`` holding a 2-D fp32 matrix split as hi + lo."""
-    __slots__ = ("t", "rows", "cols", "ld")
+    """A bf16 hi/lo plane pair holding a 2-D fp32 matrix ``[rows, cols]`` split as hi + lo.
 
-    def __init__(self, t: torch.Tensor, rows: int, cols: int, ld: int):
-        self.t, self.rows, self.cols, self.ld = t, rows, cols, ld
+    ``addr`` is the device address of element (0, 0) of the hi plane, the lo plane starts
+    ``plane_stride`` elements later; ``keep`` pins the owning torch storage."""
+    __slots__ = ("keep", "addr", "rows", "cols", "ld", "plane_stride")
+
+    def __init__(self, keep: torch.Tensor, addr: int, rows: int, cols: int, ld: int, plane_stride: int):
+        self.keep, self.addr, self.rows, self.cols, self.ld, self.plane_stride = keep, addr, rows, cols, ld, plane_stride
 
     @staticmethod
     def empty(rows: int, cols: int, device, ld: Optional[int] = None) -> "Planes":
         ld = ld if ld is not None else (cols + 7) // 8 * 8
-        return Planes(torch.empty((2, rows, ld), dtype=torch.bfloat16, device=device), rows, cols, ld)
-
-    @property
-    def plane_stride(self) -> int:
-        return self.rows * self.ld
+        t = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=device)
+        return Planes(t, t.data_ptr(), rows, cols, ld, rows * ld)
 
     def ptr(self, elem_off: int = 0) -> int:
-        return self.t.data_ptr() + 2 * elem_off
+        return self.addr + 2 * elem_off
 
     def float(self) -> torch.Tensor:
-        """hi + lo as fp32 [rows, cols] (debug / tests)."""
-        return (self.t[0].float() + self.t[1].float())[:, : self.cols]
+        """hi + lo as fp32 [rows, cols] (debug / tests; only for planes created by ``empty``)."""
+        t = self.keep.view(2, self.rows, self.ld)
+        return (t[0].float() + t[1].float())[:, : self.cols]
 
 
 def operand(ptr: int, inner: int, rows: int, ld: int, plane_stride: int, mn_major: bool = False,
@@ -225,6 +226,21 @@ def embed_loc_bwd(loc, dout, dw5, db5, dw4, db4, dw2, db2, dseq, M, H):
 def colsum(x, ld, rows, cols, out, accumulate=False):
     _check(load().yv_colsum(C.c_void_p(x.data_ptr()), C.c_int64(ld), C.c_int64(rows), C.c_int32(cols),
                             C.c_void_p(out.data_ptr()), C.c_int32(1 if accumulate else 0), _stream()), "colsum")
+
+
+def colsum_planes(p: Planes, out, accumulate=False):
+    _check(load().yv_colsum_planes(C.c_void_p(p.ptr()), C.c_int64(p.ld), C.c_int64(p.plane_stride), C.c_int64(p.rows),
+                                   C.c_int32(p.cols), C.c_void_p(out.data_ptr()), C.c_int32(1 if accumulate else 0),
+                                   _stream()), "colsum_planes")
+
+
+def act_bwd_split(dy: torch.Tensor, aux: Optional[torch.Tensor], act: int, dst: Planes):
+    """planes = dy * act'(aux); dy / aux are 2-D f32 with unit column stride."""
+    rows, cols = dy.shape
+    _check(load().yv_act_bwd_split(C.c_void_p(dy.data_ptr()), C.c_int64(dy.stride(0)), C.c_void_p(_p(aux)),
+                                   C.c_int64(aux.stride(0) if aux is not None else 0), C.c_int32(act), C.c_void_p(dst.ptr()),
+                                   C.c_int64(dst.ld), C.c_int64(dst.plane_stride), C.c_int64(rows), C.c_int64(cols),
+                                   _stream()), "act_bwd_split")
 
 
 def ce_loss(logits, ld, target, rows, cols, loss_sum, count):

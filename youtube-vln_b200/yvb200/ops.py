@@ -1,0 +1,690 @@
+"""Fused building blocks of the two-stream ViLBERT path as ``torch.autograd.Function``s over the C ABI.
+
+Each block mirrors one sub-module of the reference (vilbert/vilbert.py) and owns a hand-written backward:
+
+  DenseAct       act(x W^T + b)                          BertIntermediate :351-354, poolers :827-848, decoders
+  DenseResLN     LN(dropout(x W^T + b) + r)              Bert(Image)SelfOutput / Output :321-325,:364-368, BiOutput
+  DenseActLN     LN(gelu(x W^T + b))                     Bert(Img)PredictionHeadTransform :863-886
+  SelfAttention  QKV proj -> softmax(QK^T/sqrt(d)+m) V   Bert(Image)SelfAttention :284-311, :413-440
+  BiAttention    both cross-stream directions            BertBiAttention :552-618
+  TextEmbed      gather-sum -> LN -> dropout             BertEmbeddings :240-256
+  ImageEmbed     2048->H GEMM + location terms -> LN     BertImageEmbeddings :1356-1370
+
+All contractions run on ``yv_gemm`` (tcgen05); operands travel as bf16 hi/lo planes (bf16x3 by default so the
+end-to-end result stays within 1e-3 of the fp32 reference; YVB200_PRECISION=bf16 selects plain bf16).
+Nothing here falls back to torch math: tensors must live on a CUDA device and the library must load.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+import os
+import types
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import lib as L
+from .lib import Planes
+
+LN_EPS = 1e-12
+
+# ----------------------------------------------------------------------------------------------------
+# runtime state
+# ----------------------------------------------------------------------------------------------------
+_site_counter = itertools.count(1)
+
+
+def new_site() -> int:
+    """Unique id of a dropout call site (one per module instance), part of the RNG key."""
+    return next(_site_counter)
+
+
+class Runtime:
+    def __init__(self, device: torch.device):
+        self.device = device
+        mode = os.environ.get("YVB200_PRECISION", "bf16x3")
+        if mode not in ("bf16x3", "bf16"):
+            raise RuntimeError(f"YVB200_PRECISION must be bf16x3 or bf16, got {mode}")
+        self.passes = 3 if mode == "bf16x3" else 1
+        self.attn_passes = int(os.environ.get("YVB200_ATTN_PASSES", self.passes))
+        seed = int(os.environ.get("YVB200_SEED", "20231117"))
+        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self.arena = WeightArena(device)
+
+    def set_precision(self, mode: str):
+        self.passes = 3 if mode == "bf16x3" else 1
+        self.attn_passes = self.passes
+
+    def advance_rng(self):
+        L.rng_advance(self.rng)
+
+
+_RT: Dict[int, Runtime] = {}
+
+
+def rt(device) -> Runtime:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("yvb200 ops need CUDA tensors (no CPU fallback on this path)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    r = _RT.get(idx)
+    if r is None:
+        L.load()
+        r = _RT[idx] = Runtime(torch.device("cuda", idx))
+    return r
+
+
+# ----------------------------------------------------------------------------------------------------
+# weight arena: all GEMM weights as bf16 hi/lo planes in a few flat buffers, refreshed in one launch
+# ----------------------------------------------------------------------------------------------------
+class _Entry:
+    __slots__ = ("params", "rows", "cols", "off", "chunk", "versions", "ptrs", "planes")
+
+
+class _Chunk:
+    def __init__(self, cap: int, device):
+        self.cap = cap
+        self.used = 0
+        self.buf = torch.empty((2, cap), dtype=torch.bfloat16, device=device)
+        self.entries: List[_Entry] = []
+        self.table = None
+        self.total_blocks = 0
+        self.nseg = 0
+
+
+class WeightArena:
+    CHUNK = 96 * 1024 * 1024  # elements per plane
+
+    def __init__(self, device):
+        self.device = device
+        self.chunks: List[_Chunk] = []
+        self.entries: Dict[Tuple[int, ...], _Entry] = {}
+        self.always_stale = False      # bench: convert weights every step as real training would
+
+    def _alloc(self, n: int) -> Tuple[_Chunk, int]:
+        n_al = (n + 63) // 64 * 64
+        for c in self.chunks:
+            if c.used + n_al <= c.cap:
+                off = c.used
+                c.used += n_al
+                return c, off
+        c = _Chunk(max(self.CHUNK if self.chunks or n_al > 8 * 1024 * 1024 else 8 * 1024 * 1024, n_al), self.device)
+        self.chunks.append(c)
+        c.used = n_al
+        return c, 0
+
+    @staticmethod
+    def _fresh(e: _Entry) -> bool:
+        return len(e.versions) == len(e.params) and all(
+            p._version == v and p.data_ptr() == a for p, v, a in zip(e.params, e.versions, e.ptrs))
+
+    def _mark(self, e: _Entry):
+        e.versions = tuple(p._version for p in e.params)
+        e.ptrs = tuple(p.data_ptr() for p in e.params)
+
+    def get(self, params: Tuple[torch.Tensor, ...]) -> Planes:
+        """Planes of the row-wise concatenation of ``params`` (each [rows_i, cols], fp32)."""
+        key = tuple(id(p) for p in params)
+        e = self.entries.get(key)
+        if e is None:
+            cols = params[0].shape[1]
+            if cols % 8:
+                raise RuntimeError(f"yvb200: GEMM weight with in_features={cols} (must be a multiple of 8)")
+            e = _Entry()
+            e.params = tuple(params)
+            e.rows = sum(p.shape[0] for p in params)
+            e.cols = cols
+            e.chunk, e.off = self._alloc(e.rows * cols)
+            e.versions = e.ptrs = ()
+            e.planes = Planes(e.chunk.buf, e.chunk.buf.data_ptr() + 2 * e.off, e.rows, cols, cols, e.chunk.cap)
+            e.chunk.entries.append(e)
+            e.chunk.table = None
+            self.entries[key] = e
+        if not self._fresh(e):
+            self._refresh_entry(e)
+        return e.planes
+
+    def _refresh_entry(self, e: _Entry):
+        r0 = 0
+        for p in e.params:
+            if not (p.is_contiguous() and p.dtype == torch.float32):
+                raise RuntimeError("yvb200: weights must be contiguous fp32")
+            dst = Planes(e.chunk.buf, e.planes.addr + 2 * r0 * e.cols, p.shape[0], e.cols, e.cols, e.chunk.cap)
+            L.split_planes(p.detach(), dst)
+            r0 += p.shape[0]
+        self._mark(e)
+
+    def refresh_all(self, force: bool = False):
+        """Re-split every chunk that holds a stale entry with one ``yv_split_multi`` launch."""
+        force = force or self.always_stale
+        for c in self.chunks:
+            if not c.entries:
+                continue
+            if not force and all(self._fresh(e) for e in c.entries):
+                continue
+            ptrs = tuple(p.data_ptr() for e in c.entries for p in e.params)
+            if c.table is None or c.table[1] != ptrs:
+                rows = []
+                blk = 0
+                for e in c.entries:
+                    off = e.off
+                    for p in e.params:
+                        if not (p.is_contiguous() and p.dtype == torch.float32):
+                            raise RuntimeError("yvb200: weights must be contiguous fp32")
+                        n = p.numel()
+                        rows.append([p.data_ptr(), off, n, blk])
+                        blk += (n + 2047) // 2048
+                        off += n
+                t = torch.tensor(rows, dtype=torch.int64).to(self.device, non_blocking=False)
+                c.table = (t, ptrs)
+                c.total_blocks = blk
+                c.nseg = len(rows)
+            L.split_multi(c.table[0], c.nseg, c.total_blocks, c.buf, c.cap)
+            for e in c.entries:
+                self._mark(e)
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------
+def _c2d(x: torch.Tensor) -> torch.Tensor:
+    """[..., C] fp32 -> contiguous 2-D view (copying only when the input is not contiguous)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1]:
+        return x                       # row-strided 2-D views (e.g. hidden[:, 0]) are consumed in place
+    x2 = x.reshape(-1, x.shape[-1])
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+def attach_planes(t: torch.Tensor, p: Planes):
+    t._yv_planes = (p, t._version, t.data_ptr())
+
+
+def planes_of(x: torch.Tensor, x2: torch.Tensor) -> Planes:
+    """bf16 hi/lo planes of the 2-D view ``x2`` of ``x`` -- reuses the producer's planes when present."""
+    tag = getattr(x, "_yv_planes", None)
+    if tag is not None and tag[1] == x._version and tag[2] == x.data_ptr() and tag[0].rows == x2.shape[0] \
+            and tag[0].cols == x2.shape[1]:
+        return tag[0]
+    return L.split_planes(x2)
+
+
+def _f32(*shape, device):
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int, N: int, K: int, device,
+                need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None):
+    """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K]."""
+    dx = dW = db = None
+    if need_dx:
+        dx = _f32(M, K, device=device)
+        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
+    if need_dw:
+        dW = _f32(N, K, device=device)
+        L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
+        db = _f32(N, device=device)
+        L.colsum_planes(dp, db)
+    return dx, dW, db
+
+
+# ----------------------------------------------------------------------------------------------------
+# DenseAct
+# ----------------------------------------------------------------------------------------------------
+class DenseActFn(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, spec):
+        r = rt(x.device)
+        x2 = _c2d(x)
+        M, K = x2.shape
+        N = W.shape[0]
+        xp = planes_of(x, x2)
+        wp = r.arena.get((W,))
+        act = spec.act
+        need = any(ctx.needs_input_grad)
+        y = _f32(M, N, device=x.device)
+        yp = Planes.empty(M, N, x.device) if spec.want_planes else None
+        pre = _f32(M, N, device=x.device) if (act == L.ACT_GELU and need) else None
+        L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, act=act, aux_out=pre, out32=y, ld_out=N,
+               out_planes=yp.ptr() if yp else None, ld_pl=yp.ld if yp else 0,
+               pl_plane_stride=yp.plane_stride if yp else 0)
+        ctx.r, ctx.xp, ctx.wp, ctx.act, ctx.dims = r, xp, wp, act, (M, N, K)
+        ctx.aux = pre if act == L.ACT_GELU else (y if act == L.ACT_RELU else None)
+        ctx.xshape = x.shape
+        spec.out_planes = yp
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        r = ctx.r
+        M, N, K = ctx.dims
+        dy2 = _c2d(dy)
+        dp = Planes.empty(M, N, dy.device)
+        L.act_bwd_split(dy2, ctx.aux, ctx.act, dp)
+        dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dy.device, ctx.needs_input_grad[0],
+                                 ctx.needs_input_grad[1])
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None
+
+
+def dense_act(x, W, b, act: int, want_planes: bool = True):
+    spec = types.SimpleNamespace(act=act, want_planes=want_planes, out_planes=None)
+    y = DenseActFn.apply(x, W, b, spec)
+    if spec.out_planes is not None:
+        attach_planes(y, spec.out_planes)
+    return y
+
+
+# ----------------------------------------------------------------------------------------------------
+# DenseResLN
+# ----------------------------------------------------------------------------------------------------
+class DenseResLNFn(Function):
+    @staticmethod
+    def forward(ctx, x, res, W, b, gamma, beta, spec):
+        r = rt(x.device)
+        x2 = _c2d(x)
+        res2 = _c2d(res)
+        M, K = x2.shape
+        N = W.shape[0]
+        xp = planes_of(x, x2)
+        wp = r.arena.get((W,))
+        s = _f32(M, N, device=x.device)
+        L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, residual=res2, out32=s, ld_out=N,
+               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng)
+        z = _f32(M, N, device=x.device)
+        zp = Planes.empty(M, N, x.device)
+        stats = _f32(M, 2, device=x.device)
+        L.layernorm_fwd(s, gamma, beta, LN_EPS, z, zp, stats, M, N)
+        ctx.r, ctx.xp, ctx.wp, ctx.dims, ctx.spec = r, xp, wp, (M, N, K), spec
+        ctx.save_for_backward(s, stats, gamma)
+        ctx.xshape, ctx.rshape = x.shape, res.shape
+        spec.out_planes = zp
+        return z.view(res.shape)
+
+    @staticmethod
+    def backward(ctx, dz):
+        r, spec = ctx.r, ctx.spec
+        M, N, K = ctx.dims
+        s, stats, gamma = ctx.saved_tensors
+        dz2 = _c2d(dz)
+        dev = dz.device
+        ds = _f32(M, N, device=dev)
+        dsp = Planes.empty(M, N, dev)
+        dgamma = torch.zeros(N, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(N, dtype=torch.float32, device=dev)
+        L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, dgamma, dbeta, M, N, pre_drop_p=spec.drop_p,
+                        pre_drop_site=spec.site, rng=r.rng)
+        dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2])
+        return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, dgamma, dbeta, None
+
+
+def dense_res_ln(x, res, W, b, gamma, beta, drop_p: float, site: int):
+    spec = types.SimpleNamespace(drop_p=float(drop_p), site=site, out_planes=None)
+    z = DenseResLNFn.apply(x, res, W, b, gamma, beta, spec)
+    attach_planes(z, spec.out_planes)
+    return z
+
+
+# ----------------------------------------------------------------------------------------------------
+# DenseActLN (prediction-head transforms)
+# ----------------------------------------------------------------------------------------------------
+class DenseActLNFn(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, gamma, beta, spec):
+        r = rt(x.device)
+        x2 = _c2d(x)
+        M, K = x2.shape
+        N = W.shape[0]
+        xp = planes_of(x, x2)
+        wp = r.arena.get((W,))
+        pre = _f32(M, N, device=x.device)
+        g = _f32(M, N, device=x.device)
+        L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, act=spec.act, aux_out=pre, out32=g, ld_out=N)
+        z = _f32(M, N, device=x.device)
+        zp = Planes.empty(M, N, x.device)
+        stats = _f32(M, 2, device=x.device)
+        L.layernorm_fwd(g, gamma, beta, LN_EPS, z, zp, stats, M, N)
+        ctx.r, ctx.xp, ctx.wp, ctx.dims, ctx.act = r, xp, wp, (M, N, K), spec.act
+        ctx.save_for_backward(pre, g, stats, gamma)
+        ctx.xshape = x.shape
+        spec.out_planes = zp
+        return z.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dz):
+        r = ctx.r
+        M, N, K = ctx.dims
+        pre, g, stats, gamma = ctx.saved_tensors
+        dev = dz.device
+        dg = _f32(M, N, device=dev)
+        dgamma = torch.zeros(N, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(N, dtype=torch.float32, device=dev)
+        L.layernorm_bwd(_c2d(dz), g, gamma, stats, dg, None, dgamma, dbeta, M, N)
+        dp = Planes.empty(M, N, dev)
+        aux = pre if ctx.act == L.ACT_GELU else g
+        L.act_bwd_split(dg, aux, ctx.act, dp)
+        dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, dgamma, dbeta, None
+
+
+def dense_act_ln(x, W, b, gamma, beta, act: int):
+    spec = types.SimpleNamespace(act=act, out_planes=None)
+    z = DenseActLNFn.apply(x, W, b, gamma, beta, spec)
+    attach_planes(z, spec.out_planes)
+    return z
+
+
+# ----------------------------------------------------------------------------------------------------
+# attention core (shared by self- and bi-attention); q/k/v are "head views" into projection buffers
+# ----------------------------------------------------------------------------------------------------
+class HeadView:
+    """Columns [off, off + heads*dh) of a plane pair [pairs*S, ld] seen as [pairs, heads, S, dh]."""
+    __slots__ = ("p", "off", "S")
+
+    def __init__(self, p: Planes, off: int, S: int):
+        self.p, self.off, self.S = p, off, S
+
+    def operand(self, pairs: int, heads: int, dh: int, mn_major: bool):
+        return L.operand(self.p.ptr(self.off), dh, self.S, self.p.ld, self.p.plane_stride, mn_major, heads, dh, pairs,
+                         self.S * self.p.ld)
+
+
+def _score_operand(p: Planes, Tq: int, Tk: int, ldS: int, pairs: int, heads: int, mn_major: bool):
+    return L.operand(p.ptr(), Tk, Tq, ldS, p.plane_stride, mn_major, heads, Tq * ldS, pairs, heads * Tq * ldS)
+
+
+def _attn_fwd(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Tensor, pairs: int, heads: int, dh: int,
+              drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]):
+    Tq, Tk = q.S, k.S
+    ldS = (Tk + 7) // 8 * 8
+    dev = mask.device
+    S = _f32(pairs, heads, Tq, ldS, device=dev)
+    L.gemm(Tq, Tk, dh, q.operand(pairs, heads, dh, False), k.operand(pairs, heads, dh, False), passes=r.attn_passes,
+           out32=S, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
+    rows = pairs * heads * Tq
+    Pp = Planes.empty(rows, Tk, dev, ld=ldS)
+    L.softmax_fwd(S, ldS, mask, rows, Tk, heads * Tq, 1.0 / math.sqrt(dh), Pp, drop_p, site, r.rng)
+    Hout = heads * dh
+    L.gemm(Tq, dh, Tk, _score_operand(Pp, Tq, Tk, ldS, pairs, heads, False), v.operand(pairs, heads, dh, True),
+           passes=r.attn_passes, out32=ctx32, ld_out=Hout, out_sb0=dh, out_sb1=Tq * Hout, out_planes=ctxp.ptr(),
+           ld_pl=ctxp.ld, pl_sb0=dh, pl_sb1=Tq * ctxp.ld, pl_plane_stride=ctxp.plane_stride)
+    return S, Pp
+
+
+def _attn_bwd(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, P: torch.Tensor, Pp: Planes, pairs: int,
+              heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView):
+    Tq, Tk = q.S, k.S
+    ldS = P.shape[-1]
+    dev = P.device
+    rows = pairs * heads * Tq
+    dO = HeadView(dOp, 0, Tq)
+    # dPd = dO . V^T
+    dPd = _f32(pairs, heads, Tq, ldS, device=dev)
+    L.gemm(Tq, Tk, dh, dO.operand(pairs, heads, dh, False), v.operand(pairs, heads, dh, False), passes=r.attn_passes,
+           out32=dPd, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
+
+    def out_view(hv: HeadView):
+        return dict(out_planes=hv.p.ptr(hv.off), ld_pl=hv.p.ld, pl_sb0=dh, pl_sb1=hv.S * hv.p.ld,
+                    pl_plane_stride=hv.p.plane_stride)
+
+    # dV = Pd^T . dO     [Tk, dh], contraction over Tq
+    L.gemm(Tk, dh, Tq, _score_operand(Pp, Tq, Tk, ldS, pairs, heads, True), dO.operand(pairs, heads, dh, True),
+           passes=r.attn_passes, **out_view(dv))
+    dSp = Planes.empty(rows, Tk, dev, ld=ldS)
+    L.softmax_bwd(P, dPd, ldS, rows, Tk, 1.0 / math.sqrt(dh), dSp, drop_p, site, r.rng)
+    # dQ = dS . K        [Tq, dh], contraction over Tk
+    L.gemm(Tq, dh, Tk, _score_operand(dSp, Tq, Tk, ldS, pairs, heads, False), k.operand(pairs, heads, dh, True),
+           passes=r.attn_passes, **out_view(dq))
+    # dK = dS^T . Q      [Tk, dh], contraction over Tq
+    L.gemm(Tk, dh, Tq, _score_operand(dSp, Tq, Tk, ldS, pairs, heads, True), q.operand(pairs, heads, dh, True),
+           passes=r.attn_passes, **out_view(dk))
+
+
+def _mask2d(mask: torch.Tensor, pairs: int, Tk: int) -> torch.Tensor:
+    """The reference passes the additive mask as [N,1,1,S] (vilbert/vilbert.py:1268-1287)."""
+    if mask.numel() != pairs * Tk:
+        raise RuntimeError(f"yvb200: attention mask of shape {tuple(mask.shape)} is not [N,1,1,{Tk}]")
+    m = mask.reshape(pairs, Tk)
+    if m.dtype != torch.float32:
+        m = m.float()
+    return m.contiguous()
+
+
+def _cat_bias(bs):
+    return torch.cat([b.detach() for b in bs])
+
+
+class SelfAttentionFn(Function):
+    @staticmethod
+    def forward(ctx, x, mask, Wq, bq, Wk, bk, Wv, bv, spec):
+        r = rt(x.device)
+        pairs, S, K = x.shape
+        H = Wq.shape[0]
+        heads = spec.heads
+        dh = H // heads
+        x2 = _c2d(x)
+        M = pairs * S
+        xp = planes_of(x, x2)
+        wp = r.arena.get((Wq, Wk, Wv))
+        m2 = _mask2d(mask, pairs, S)
+        qkv = Planes.empty(M, 3 * H, x.device)
+        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=_cat_bias((bq, bk, bv)),
+               out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
+        c32 = _f32(M, H, device=x.device)
+        cp = Planes.empty(M, H, x.device)
+        q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
+        P, Pp = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, c32)
+        ctx.r, ctx.xp, ctx.wp, ctx.qkv, ctx.Pp, ctx.spec = r, xp, wp, qkv, Pp, spec
+        ctx.dims = (pairs, S, K, H, heads, dh)
+        ctx.save_for_backward(P)
+        spec.out_planes = cp
+        spec.probs = P
+        return c32.view(pairs, S, H)
+
+    @staticmethod
+    def backward(ctx, dc):
+        r, spec = ctx.r, ctx.spec
+        pairs, S, K, H, heads, dh = ctx.dims
+        (P,) = ctx.saved_tensors
+        M = pairs * S
+        dev = dc.device
+        dOp = L.split_planes(_c2d(dc))
+        dqkv = Planes.empty(M, 3 * H, dev)
+        qkv = ctx.qkv
+        q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
+        _attn_bwd(r, dOp, q, k, v, P, ctx.Pp, pairs, heads, dh, spec.drop_p, spec.site,
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
+        dx, dW, db = _linear_bwd(r, dqkv, ctx.xp, ctx.wp, M, 3 * H, K, dev, ctx.needs_input_grad[0], True)
+        return ((dx.view(pairs, S, K) if dx is not None else None), None,
+                dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:], None)
+
+
+def self_attention(x, mask, Wq, bq, Wk, bk, Wv, bv, heads: int, drop_p: float, site: int):
+    spec = types.SimpleNamespace(heads=heads, drop_p=float(drop_p), site=site, out_planes=None, probs=None)
+    c = SelfAttentionFn.apply(x, mask, Wq, bq, Wk, bk, Wv, bv, spec)
+    attach_planes(c, spec.out_planes)
+    return c, spec.probs
+
+
+class BiAttentionFn(Function):
+    """vision stream = "1", text stream = "2" as in the reference: ctx1 = softmax(q2 k1^T) v1 (text attends vision),
+    ctx2 = softmax(q1 k2^T) v2 (vision attends text)."""
+
+    @staticmethod
+    def forward(ctx, xv, vmask, xt, tmask, Wq1, bq1, Wk1, bk1, Wv1, bv1, Wq2, bq2, Wk2, bk2, Wv2, bv2, spec):
+        r = rt(xv.device)
+        pairs, V, Kv = xv.shape
+        _, T, Kt = xt.shape
+        H = Wq1.shape[0]
+        heads = spec.heads
+        dh = H // heads
+        dev = xv.device
+        xv2, xt2 = _c2d(xv), _c2d(xt)
+        Mv, Mt = pairs * V, pairs * T
+        xvp, xtp = planes_of(xv, xv2), planes_of(xt, xt2)
+        w1 = r.arena.get((Wq1, Wk1, Wv1))
+        w2 = r.arena.get((Wq2, Wk2, Wv2))
+        qkv1 = Planes.empty(Mv, 3 * H, dev)
+        qkv2 = Planes.empty(Mt, 3 * H, dev)
+        L.gemm(Mv, 3 * H, Kv, L.op_of(xvp), L.op_of(w1), passes=r.passes, bias=_cat_bias((bq1, bk1, bv1)),
+               out_planes=qkv1.ptr(), ld_pl=qkv1.ld, pl_plane_stride=qkv1.plane_stride)
+        L.gemm(Mt, 3 * H, Kt, L.op_of(xtp), L.op_of(w2), passes=r.passes, bias=_cat_bias((bq2, bk2, bv2)),
+               out_planes=qkv2.ptr(), ld_pl=qkv2.ld, pl_plane_stride=qkv2.plane_stride)
+        vm, tm = _mask2d(vmask, pairs, V), _mask2d(tmask, pairs, T)
+        c1 = _f32(Mt, H, device=dev)
+        c1p = Planes.empty(Mt, H, dev)
+        c2 = _f32(Mv, H, device=dev)
+        c2p = Planes.empty(Mv, H, dev)
+        q1, k1, v1 = HeadView(qkv1, 0, V), HeadView(qkv1, H, V), HeadView(qkv1, 2 * H, V)
+        q2, k2, v2 = HeadView(qkv2, 0, T), HeadView(qkv2, H, T), HeadView(qkv2, 2 * H, T)
+        P1, P1p = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
+        P2, P2p = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2)
+        ctx.r, ctx.spec = r, spec
+        ctx.keep = (xvp, xtp, w1, w2, qkv1, qkv2, P1p, P2p)
+        ctx.dims = (pairs, V, T, Kv, Kt, H, heads, dh)
+        ctx.save_for_backward(P1, P2)
+        spec.out_planes = (c1p, c2p)
+        spec.probs = (P1, P2)
+        return c1.view(pairs, T, H), c2.view(pairs, V, H)
+
+    @staticmethod
+    def backward(ctx, dc1, dc2):
+        r, spec = ctx.r, ctx.spec
+        pairs, V, T, Kv, Kt, H, heads, dh = ctx.dims
+        xvp, xtp, w1, w2, qkv1, qkv2, P1p, P2p = ctx.keep
+        P1, P2 = ctx.saved_tensors
+        dev = dc1.device
+        Mv, Mt = pairs * V, pairs * T
+        dO1 = L.split_planes(_c2d(dc1))
+        dO2 = L.split_planes(_c2d(dc2))
+        d1 = Planes.empty(Mv, 3 * H, dev)
+        d2 = Planes.empty(Mt, 3 * H, dev)
+        q1, k1, v1 = HeadView(qkv1, 0, V), HeadView(qkv1, H, V), HeadView(qkv1, 2 * H, V)
+        q2, k2, v2 = HeadView(qkv2, 0, T), HeadView(qkv2, H, T), HeadView(qkv2, 2 * H, T)
+        dq1, dk1, dv1 = HeadView(d1, 0, V), HeadView(d1, H, V), HeadView(d1, 2 * H, V)
+        dq2, dk2, dv2 = HeadView(d2, 0, T), HeadView(d2, H, T), HeadView(d2, 2 * H, T)
+        _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
+        _attn_bwd(r, dO2, q1, k2, v2, P2, P2p, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2)
+        dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True)
+        dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True)
+        return ((dxv.view(pairs, V, Kv) if dxv is not None else None), None,
+                (dxt.view(pairs, T, Kt) if dxt is not None else None), None,
+                dW1[:H], db1[:H], dW1[H:2 * H], db1[H:2 * H], dW1[2 * H:], db1[2 * H:],
+                dW2[:H], db2[:H], dW2[H:2 * H], db2[H:2 * H], dW2[2 * H:], db2[2 * H:], None)
+
+
+def bi_attention(xv, vmask, xt, tmask, params1, params2, heads: int, drop_p1: float, site1: int, drop_p2: float,
+                 site2: int):
+    spec = types.SimpleNamespace(heads=heads, drop_p1=float(drop_p1), site1=site1, drop_p2=float(drop_p2), site2=site2,
+                                 out_planes=None, probs=None)
+    c1, c2 = BiAttentionFn.apply(xv, vmask, xt, tmask, *params1, *params2, spec)
+    attach_planes(c1, spec.out_planes[0])
+    attach_planes(c2, spec.out_planes[1])
+    return c1, c2, spec.probs
+
+
+# ----------------------------------------------------------------------------------------------------
+# embeddings
+# ----------------------------------------------------------------------------------------------------
+class TextEmbedFn(Function):
+    @staticmethod
+    def forward(ctx, tok, seg, word, pos, typ, gamma, beta, spec):
+        r = rt(word.device)
+        pairs, T = tok.shape
+        H = word.shape[1]
+        M = pairs * T
+        dev = word.device
+        tok_c, seg_c = tok.contiguous().long(), seg.contiguous().long()
+        e = _f32(M, H, device=dev)
+        L.embed_text_fwd(tok_c, seg_c, word, pos, typ, e, M, T, H)
+        y = _f32(M, H, device=dev)
+        yp = Planes.empty(M, H, dev)
+        stats = _f32(M, 2, device=dev)
+        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, r.rng)
+        ctx.r, ctx.spec, ctx.dims = r, spec, (pairs, T, H)
+        ctx.shapes = (word.shape, pos.shape, typ.shape)
+        ctx.save_for_backward(tok_c, seg_c, e, stats, gamma)
+        spec.out_planes = yp
+        return y.view(pairs, T, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        r, spec = ctx.r, ctx.spec
+        pairs, T, H = ctx.dims
+        tok, seg, e, stats, gamma = ctx.saved_tensors
+        M = pairs * T
+        dev = dy.device
+        de = _f32(M, H, device=dev)
+        dgamma = torch.zeros(H, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(H, dtype=torch.float32, device=dev)
+        L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, None, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
+                        post_drop_site=spec.site, rng=r.rng)
+        dword = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev)
+        dpos = torch.zeros(ctx.shapes[1], dtype=torch.float32, device=dev)
+        dtyp = torch.zeros(ctx.shapes[2], dtype=torch.float32, device=dev)
+        L.embed_text_bwd(tok, seg, de, dword, dpos, dtyp, M, T, H, spec.padding_idx)
+        return None, None, dword, dpos, dtyp, dgamma, dbeta, None
+
+
+def text_embed(tok, seg, word, pos, typ, gamma, beta, drop_p: float, site: int, padding_idx: int = 0):
+    spec = types.SimpleNamespace(drop_p=float(drop_p), site=site, padding_idx=padding_idx, out_planes=None)
+    y = TextEmbedFn.apply(tok, seg, word, pos, typ, gamma, beta, spec)
+    attach_planes(y, spec.out_planes)
+    return y
+
+
+class ImageEmbedFn(Function):
+    @staticmethod
+    def forward(ctx, feat, loc, Wi, bi, w5, b5, w4, b4, w2, b2, seq, gamma, beta, spec):
+        r = rt(Wi.device)
+        pairs, V, F = feat.shape
+        H = Wi.shape[0]
+        M = pairs * V
+        dev = Wi.device
+        f2 = _c2d(feat)
+        fp = planes_of(feat, f2)
+        loc2 = _c2d(loc)
+        if loc2.shape[1] != 12:
+            raise RuntimeError("yvb200: image_loc must have 12 columns (5 box + 4 orientation + 2 next + frame index)")
+        le = _f32(M, H, device=dev)
+        L.embed_loc_fwd(loc2, w5, b5, w4, b4, w2, b2, seq, le, M, H)
+        wp = r.arena.get((Wi,))
+        e = _f32(M, H, device=dev)
+        L.gemm(M, H, F, L.op_of(fp), L.op_of(wp), passes=r.passes, bias=bi, residual=le, out32=e, ld_out=H)
+        y = _f32(M, H, device=dev)
+        yp = Planes.empty(M, H, dev)
+        stats = _f32(M, 2, device=dev)
+        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, r.rng)
+        ctx.r, ctx.spec, ctx.dims, ctx.fp, ctx.wp = r, spec, (pairs, V, F, H), fp, wp
+        ctx.save_for_backward(loc2, e, stats, gamma)
+        spec.out_planes = yp
+        return y.view(pairs, V, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        r, spec = ctx.r, ctx.spec
+        pairs, V, F, H = ctx.dims
+        loc2, e, stats, gamma = ctx.saved_tensors
+        M = pairs * V
+        dev = dy.device
+        de = _f32(M, H, device=dev)
+        dep = Planes.empty(M, H, dev)
+        dgamma = torch.zeros(H, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(H, dtype=torch.float32, device=dev)
+        L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, dep, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
+                        post_drop_site=spec.site, rng=r.rng)
+        dfeat, dWi, dbi = _linear_bwd(r, dep, ctx.fp, ctx.wp, M, H, F, dev, ctx.needs_input_grad[0], True)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        dw5, db5, dw4, db4, dw2, db2, dseq = z(H, 5), z(H), z(H, 4), z(H), z(H, 2), z(H), z(32, H)
+        L.embed_loc_bwd(loc2, de, dw5, db5, dw4, db4, dw2, db2, dseq, M, H)
+        return ((dfeat.view(pairs, V, F) if dfeat is not None else None), None, dWi, dbi, dw5, db5, dw4, db4, dw2, db2,
+                dseq, dgamma, dbeta, None)
+
+
+def image_embed(feat, loc, Wi, bi, w5, b5, w4, b4, w2, b2, seq, gamma, beta, drop_p: float, site: int):
+    spec = types.SimpleNamespace(drop_p=float(drop_p), site=site, out_planes=None)
+    y = ImageEmbedFn.apply(feat, loc, Wi, bi, w5, b5, w4, b4, w2, b2, seq, gamma, beta, spec)
+    attach_planes(y, spec.out_planes)
+    return y
