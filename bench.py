@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-instruction pairs/sec of the ViLBERT training step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (B200 kernels, one process per GPU)
+  python bench.py --impl reference --gpus N ...            reference arm: the CPU oracle port on host cores
+
+A step = forward + masked_vision + masked_language + ranking + traj losses + backward on one cfg2 batch
+(8 pairs x 8 frames x 36 regions x 80 tokens, full 12/6/6-layer ViLBERT), train mode (dropout on), weights
+re-split to bf16 planes every step.  `value` times K graph replays with inputs resident in HBM (CUDA events,
+L2 flushed between steps, max over ranks); `e2e` adds the pinned-host -> device copy of the batch and the
+device -> host read of the loss inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "youtube-vln_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "trajectory-instruction pairs/sec"
+UNIT = "pairs/s"
+WORKLOAD = "cfg2"
+TRAIN_GFLOP_PER_PAIR = 223.93          # 6 x 37.322 GMAC (fwd + dgrad + wgrad)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p.get("bf16_tflops_sustained", 1382.5)), float(p.get("hbm_gbs", 6538.3)), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [x for x in sm if mx and x > 0.3 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_cpu_oracle(steps, warmup, threads=None):
+    """fwd + losses + bwd of the oracle port on the host cores; returns (pairs/s, seconds per step, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vilbert_oracle as O
+    from yvb200 import synth
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS[synth.WORKLOADS[WORKLOAD]["config"]]
+    args = synth.workload_args(WORKLOAD)
+    sd = synth.lily_state_dict(cfg, seed=0)
+    batch = synth.make_batch(WORKLOAD, seed=1)
+    n = synth.num_pairs(batch)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.oracle_step(sd, cfg, args, batch, dtype=torch.float32, want_grads=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return n / sec, sec, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("YVB200_PRECISION", "bf16x3"), choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from yvb200 import synth
+    wl = synth.WORKLOADS[WORKLOAD]
+    pairs = wl["bs"] * wl["cands"]
+    config = {"workload": f"{WORKLOAD}: full ViLBERT 12t/6v/6c pretrain step (vision+language+ranking+traj), "
+                          f"{wl['frames']} frames x {wl['boxes']} regions, {wl['tokens']} tokens, {pairs} pairs/GPU",
+              "pairs_per_gpu": pairs, "parallelism": f"dp{a.gpus}", "precision": a.precision,
+              "l2": "flushed between timed steps (256 MB write); per-step working set ~3 GB >> 126 MB L2"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        k, w = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+        v, sec, cores = run_cpu_oracle(k, w)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": k, "warmup": w,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{k} full cfg2 steps (8 pairs each, eval-mode dropout) of the CPU oracle "
+                                           "restatement of vilbert/vilbert.py + get_loss_correct; the Python reference "
+                                           "itself cannot travel to the GPU box"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for --impl ours (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["YVB200_PRECISION"] = a.precision
+    from yvb200 import lib, ops
+    from yvb200.lily_compat import build_lily
+    from yvb200.step import GraphedStep
+    ops.rt(dev).set_precision(a.precision)
+    cfg = synth.CONFIGS[wl["config"]]
+    args = synth.workload_args(WORKLOAD)
+    model = build_lily(cfg, args, device=dev).train()
+    host_batch = [t.pin_memory() if torch.is_tensor(t) else t for t in synth.make_batch(WORKLOAD, seed=1, rank=rank)]
+    step = GraphedStep(model, args, host_batch, use_graph=not a.no_graph)
+
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = None
+    if world > 1:
+        import torch.distributed as dist
+        # data-parallel gradient exchange: one NCCL allreduce over a flat view of every gradient
+        flat = torch.zeros(sum(g.numel() for g in grads), dtype=torch.float32, device=dev)
+
+    def allreduce():
+        if world > 1:
+            torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat.div_(world)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(a.warmup):
+        step.run()
+        allreduce()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    barrier()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.run()
+        allreduce()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_dev = sum(x.elapsed_time(y) for x, y in evs) / 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public step API: pinned host batch -> device, loss -> host, every step
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    barrier()
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step.load(host_batch)
+        loss = step.run()
+        allreduce()
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_e2e = sum(x.elapsed_time(y) for x, y in evs) / 1e3
+    final_loss = float(loss_host[0])
+
+    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (yv_gemm): one instrumented eager step, GPU kept busy-ahead
+    peak_tf, peak_bw, peak_src = peaks()
+    lib.GEMM_TRACE = []
+    eager = GraphedStep(model, args, host_batch, use_graph=False, warmup=1)
+    lib.GEMM_TRACE = []
+    torch.cuda._sleep(int(3e8))
+    eager.run()
+    torch.cuda.synchronize(dev)
+    trace, lib.GEMM_TRACE = lib.GEMM_TRACE, None
+    g_ms = sum(e0.elapsed_time(e1) for *_, e0, e1 in trace)
+    g_flop = sum(2.0 * M * N * K * B for M, N, K, B, _, _, _ in trace)
+    hw_mult = 3.0 if a.precision == "bf16x3" else 1.0
+    achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "yv_gemm_kernel (all launches of one step)", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained", "launches": len(trace), "ms_per_step_in_kernel": g_ms,
+                "algorithmic_gflop_per_step": g_flop / 1e9, "tensor_pipe_flop_multiplier": hw_mult,
+                "frac_of_tensor_pipe": achieved * hw_mult / peak_tf}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, sec, cores = run_cpu_oracle(2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2 full cfg2 steps (8 pairs each) after 1 warm-up, fwd+losses+bwd of the CPU oracle port"}
+
+    total_pairs = pairs * world * a.steps
+    value = total_pairs / t_dev
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.precision, "data": "synthetic", "config": config,
+            "e2e": {"value": total_pairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / a.steps * 1e3},
+            "gpu_launches": step.launches_per_step * a.steps, "gpu_launches_per_step": step.launches_per_step,
+            "cuda_graph": not a.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "train_tflops_algorithmic": value * TRAIN_GFLOP_PER_PAIR / 1e3, "final_loss": final_loss}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,35 @@ YV_DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_by
     return d;
 }
 
+// one output element through the whole epilogue (ragged tile edges and unaligned leading dimensions only)
+__device__ __noinline__ void epilogue_scalar(const KParams& p, const YvDrop& drop, float acc, int n, int z, int row,
+                                             long long obase, long long pbase) {
+    if (n >= p.N) return;
+    float x = p.alpha * acc;
+    if (p.bias) x += __ldg(p.bias + n);
+    if (p.aux_out) p.aux_out[obase + n] = x;
+    if (p.act == YV_ACT_GELU) x = yv_gelu(x);
+    else if (p.act == YV_ACT_RELU) x = fmaxf(x, 0.f);
+    if (drop.thresh) x *= yv_drop_mul(drop, (uint32_t)(((long long)z * p.M + row) * p.N + n));
+    if (p.act == YV_ACT_MUL_GELU_GRAD) x *= yv_gelu_grad(p.aux_in[obase + n]);
+    else if (p.act == YV_ACT_MUL_RELU_MASK) x = p.aux_in[obase + n] > 0.f ? x : 0.f;
+    if (p.residual) x += p.residual[obase + n];
+    if (p.out32) p.out32[obase + n] = x;
+    if (p.out_planes) {
+        __nv_bfloat16 h, l;
+        yv_split(x, h, l);
+        p.out_planes[pbase + n] = h;
+        p.out_planes[pbase + n + p.pl_plane_stride] = l;
+    }
+}
+
+#ifdef YV_GEMM_TIMING
+__device__ long long yv_dbg[32];
+#define YV_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) yv_dbg[i] = clock64(); } while (0)
+#else
+#define YV_T(i)
+#endif
+
 // ------------------------------------------------------------------------------------------- kernel
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -149,6 +178,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int z = blockIdx.z;
     const int b0 = z % p.nb0, b1 = z / p.nb0;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    if (threadIdx.x == 0) YV_T(0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -170,6 +200,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) YV_T(1);
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -218,6 +249,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t accum = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(full_bar(stage), phase);
+                if (kb == 0) YV_T(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
                 uint64_t da[2], db[2];
@@ -245,6 +277,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     phase ^= 1u;
                 }
             }
+            YV_T(3);
             umma_commit(tmem_full_bar);          // accumulator complete -> epilogue
         }
     } else {
@@ -252,6 +285,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int row = m0 + q * 32 + lane;
         mbar_wait(tmem_full_bar, 0);
+        if (threadIdx.x == 64) YV_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
         const bool row_ok = row < p.M;
@@ -259,7 +293,9 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long pbase = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1 + (long long)row * p.ld_pl;
         const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.out_sb0 & 3) == 0) && ((p.out_sb1 & 3) == 0) &&
                             ((p.ld_pl & 7) == 0) && ((p.pl_sb0 & 7) == 0) && ((p.pl_sb1 & 7) == 0) &&
-                            ((p.pl_plane_stride & 7) == 0);
+                            ((p.pl_plane_stride & 7) == 0) &&
+                            (((uintptr_t)p.out32 | (uintptr_t)p.aux_out | (uintptr_t)p.aux_in | (uintptr_t)p.residual |
+                              (uintptr_t)p.bias | (uintptr_t)p.out_planes) & 15) == 0;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             const int nc = n0 + c * 32;
@@ -267,62 +303,90 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
             if (!row_ok) continue;
-            float v[32];
             const bool full = (nc + 32 <= p.N) && vec_ok;
+            if (!full) {                                     // ragged edge / unaligned rows: scalar path
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nc + j;
-                float x = p.alpha * __uint_as_float(raw[j]);
-                if (n < p.N) {
-                    if (p.bias) x += __ldg(p.bias + n);
-                    if (p.aux_out) p.aux_out[obase + n] = x;
-                    if (p.act == YV_ACT_GELU) x = yv_gelu(x);
-                    else if (p.act == YV_ACT_RELU) x = fmaxf(x, 0.f);
-                    if (drop.thresh)
-                        x *= yv_drop_mul(drop, (uint32_t)(((long long)z * p.M + row) * p.N + n));
-                    if (p.act == YV_ACT_MUL_GELU_GRAD) x *= yv_gelu_grad(p.aux_in[obase + n]);
-                    else if (p.act == YV_ACT_MUL_RELU_MASK) x = p.aux_in[obase + n] > 0.f ? x : 0.f;
-                    if (p.residual) x += p.residual[obase + n];
+                for (int j = 0; j < 32; ++j)
+                    epilogue_scalar(p, drop, __uint_as_float(raw[j]), nc + j, z, row, obase, pbase);
+                continue;
+            }
+            // each feature is a separate uniform branch around a 32-wide register loop, so only the code of
+            // the features in use is ever fetched (a per-element branch ladder thrashed the I-cache)
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[j]);
+            if (p.bias) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = __ldg(b4 + j);
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                 }
-                v[j] = x;
+            }
+            if (p.aux_out) {
+                float4* o = reinterpret_cast<float4*>(p.aux_out + obase + nc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.act == YV_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = yv_gelu(v[j]);
+            } else if (p.act == YV_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (drop.thresh) {
+                const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + nc);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= yv_drop_mul(drop, i0 + j);
+            }
+            if (p.act == YV_ACT_MUL_GELU_GRAD || p.act == YV_ACT_MUL_RELU_MASK) {
+                const float4* a4 = reinterpret_cast<const float4*>(p.aux_in + obase + nc);
+                const bool gelu = p.act == YV_ACT_MUL_GELU_GRAD;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = a4[j];
+                    if (gelu) {
+                        v[4 * j] *= yv_gelu_grad(t.x); v[4 * j + 1] *= yv_gelu_grad(t.y);
+                        v[4 * j + 2] *= yv_gelu_grad(t.z); v[4 * j + 3] *= yv_gelu_grad(t.w);
+                    } else {
+                        v[4 * j] = t.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = t.y > 0.f ? v[4 * j + 1] : 0.f;
+                        v[4 * j + 2] = t.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = t.w > 0.f ? v[4 * j + 3] : 0.f;
+                    }
+                }
+            }
+            if (p.residual) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.residual + obase + nc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = r4[j];
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
             }
             if (p.out32) {
-                if (full) {
-                    float4* o = reinterpret_cast<float4*>(p.out32 + obase + nc);
+                float4* o = reinterpret_cast<float4*>(p.out32 + obase + nc);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                } else {
-                    for (int j = 0; j < 32; ++j)
-                        if (nc + j < p.N) p.out32[obase + nc + j] = v[j];
-                }
+                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             if (p.out_planes) {
                 __nv_bfloat16* hi = p.out_planes + pbase + nc;
                 __nv_bfloat16* lo = hi + p.pl_plane_stride;
-                if (full) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __align__(16) __nv_bfloat16 h8[8], l8[8];
+                for (int j = 0; j < 4; ++j) {
+                    __align__(16) __nv_bfloat16 h8[8], l8[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) yv_split(v[8 * j + t], h8[t], l8[t]);
-                        reinterpret_cast<uint4*>(hi)[j] = *reinterpret_cast<uint4*>(h8);
-                        reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
-                    }
-                } else {
-                    for (int j = 0; j < 32; ++j)
-                        if (nc + j < p.N) {
-                            __nv_bfloat16 h, l;
-                            yv_split(v[j], h, l);
-                            hi[j] = h;
-                            lo[j] = l;
-                        }
+                    for (int t = 0; t < 8; ++t) yv_split(v[8 * j + t], h8[t], l8[t]);
+                    reinterpret_cast<uint4*>(hi)[j] = *reinterpret_cast<uint4*>(h8);
+                    reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
                 }
             }
         }
     }
 
+    if (threadIdx.x == 64) YV_T(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) YV_T(6);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS)
                      : "memory");

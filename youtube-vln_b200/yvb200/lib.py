@@ -49,6 +49,8 @@ class YvSplitSeg(C.Structure):
 
 
 _lib = None
+#: when set to a list, ``gemm`` appends (M, N, K, batch, passes, start_event, end_event) per launch
+GEMM_TRACE = None
 
 
 def load():
@@ -141,7 +143,14 @@ def gemm(M: int, N: int, K: int, a: YvOperand, b: YvOperand, *, passes: int = 3,
     g.out_planes = out_planes
     g.ld_pl, g.pl_sb0, g.pl_sb1, g.pl_plane_stride = ld_pl, pl_sb0, pl_sb1, pl_plane_stride
     g.drop_p, g.drop_site, g.rng = drop_p, drop_site, _p(rng)
-    _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
+    if GEMM_TRACE is None:
+        _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
+    else:   # bench.py's roofline leg: bracket every GEMM launch with CUDA events on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
+        e1.record()
+        GEMM_TRACE.append((M, N, K, int(a.nb0 * a.nb1), passes, e0, e1))
 
 
 def split_planes(src: torch.Tensor, dst: Optional[Planes] = None) -> Planes:

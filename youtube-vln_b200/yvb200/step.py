@@ -1,0 +1,92 @@
+"""Whole training step (forward + all active losses + backward) as one replayable CUDA graph.
+
+The reference's step (utils/utils_init.py:199-239) issues ~8k ATen ops from Python; here the step is a fixed
+sequence of yvb200 kernels, so it is captured once per batch shape and replayed with a single launch.  Inputs are
+copied into static device buffers (the host->device boundary of utils/utils_init.py:201-204), the dropout RNG step
+counter is advanced inside the graph, and every weight is re-split to bf16 planes inside the graph (weights change
+every optimiser step).  Gradients land in the parameters' ``.grad`` (static storage owned by the graph pool).
+"""
+from typing import List, Optional
+
+import torch
+
+from . import fused, lib, ops, synth
+
+_FLOAT_FIELDS = (1, 2, 4)          # image_features, image_locations, image_targets
+
+
+class GraphedStep:
+    def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
+                 refresh_weights_each_step: bool = True, warmup: int = 2):
+        self.model, self.args = model, args
+        self.device = next(model.parameters()).device
+        self.rt = ops.rt(self.device)
+        self.refresh = refresh_weights_each_step
+        self.static = [t.to(self.device).clone() if torch.is_tensor(t) else t for t in example_batch]
+        if not bool(self.static[13].all()):
+            raise RuntimeError("GraphedStep needs batches without padded candidates (opt_mask all ones)")
+        self.loss = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self.use_graph = use_graph
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._zero_grads()
+                self._body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if use_graph:
+            self._zero_grads()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.launches_per_step = lib.launch_count() - n0
+        else:
+            n0 = lib.launch_count()
+            self._zero_grads()
+            self._body()
+            self.launches_per_step = lib.launch_count() - n0
+
+    def _zero_grads(self):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def _body(self):
+        self.rt.advance_rng()
+        if self.refresh:
+            self.rt.arena.refresh_all(force=True)
+        b = self.static
+        co = b[11]
+        inputs = (b[6].flatten(0, 1), b[1].flatten(0, 1), b[2].flatten(0, 1), b[10].flatten(0, 1), b[7].flatten(0, 1),
+                  b[3].flatten(0, 1), co.reshape(-1, co.size(2), co.size(3)), b[9].flatten(0, 1), b[15])
+        out = self.model(*inputs)
+        ld = fused.step_losses(b, out, self.args, training=True, flat=True)
+        tot = 0.0
+        for k in ("vision", "language", "ranking"):
+            if k in ld:
+                tot = tot + ld[k]
+        if "traj" in ld:
+            tot = tot + self.args.traj_loss_scale * ld["traj"]
+        tot.backward()
+        self.loss = tot.detach()
+
+    def load(self, batch: List[torch.Tensor]):
+        """Copy a (pinned host or device) batch into the static buffers (async on the current stream)."""
+        for dst, src in zip(self.static, batch):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.static if torch.is_tensor(t))
+
+    def run(self) -> torch.Tensor:
+        """One step on the data currently in the static buffers; returns the (device) total loss."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._zero_grads()
+            self._body()
+        return self.loss
