@@ -5,7 +5,7 @@
 // One CTA per 128x128 output tile, 192 threads:
 //   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d with 128B swizzle into a 3/6-stage ring
 //   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), commits to mbarriers
-//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns, thread owns one output row
+//   warps 2-9: epilogue -- tcgen05.ld 32x32 chunks, transposed through swizzled smem for coalesced I/O
 // Operands may be K-major or MN-major (transposed views): dgrad / wgrad / attention products need no
 // explicit transposes.  Out-of-bounds rows/cols/k are zero-filled by TMA (each batch dim is its own
 // tensor-map dim), so ragged shapes (T=80, vocab 30522, 1601 classes) need no padding copies.
@@ -25,7 +25,7 @@ constexpr int BLOCK_N = 128;
 constexpr int BLOCK_K = 64;                                   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 16 KB (A and B tiles have the same size)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                               // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 128;
 
 template <int PASSES>
@@ -282,104 +282,100 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===================================== epilogue ==========================================
+        // 8 warps: two per TMEM lane quarter, each owning 64 of the tile's 128 columns as two 32x32 chunks.
+        // A chunk goes TMEM -> registers (thread = row) -> XOR-swizzled smem (the drained pipeline stage 0)
+        // -> registers (8 lanes = one 128-byte row segment), so every global access below is coalesced.
+        const int ew = warp - 2;
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        const int half = ew >> 2;
         mbar_wait(tmem_full_bar, 0);
         if (threadIdx.x == 64) YV_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
-        const bool row_ok = row < p.M;
-        const long long obase = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1 + (long long)row * p.ld_out;
-        const long long pbase = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1 + (long long)row * p.ld_pl;
+        const uint32_t stg = smem_base + (uint32_t)ew * 4096u;
+        const long long obatch = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1;
+        const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
         const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.out_sb0 & 3) == 0) && ((p.out_sb1 & 3) == 0) &&
-                            ((p.ld_pl & 7) == 0) && ((p.pl_sb0 & 7) == 0) && ((p.pl_sb1 & 7) == 0) &&
-                            ((p.pl_plane_stride & 7) == 0) &&
+                            ((p.ld_pl & 3) == 0) && ((p.pl_sb0 & 3) == 0) && ((p.pl_sb1 & 3) == 0) &&
+                            ((p.pl_plane_stride & 3) == 0) &&
                             (((uintptr_t)p.out32 | (uintptr_t)p.aux_out | (uintptr_t)p.aux_in | (uintptr_t)p.residual |
-                              (uintptr_t)p.bias | (uintptr_t)p.out_planes) & 15) == 0;
+                              (uintptr_t)p.bias) & 15) == 0 && (((uintptr_t)p.out_planes) & 7) == 0;
+        const int cg = lane & 7;                             // float4 column group of this lane inside a chunk
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
             const int nc = n0 + c * 32;
             if (nc >= p.N) break;                            // warp-uniform
             uint32_t raw[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-            if (!row_ok) continue;
-            const bool full = (nc + 32 <= p.N) && vec_ok;
-            if (!full) {                                     // ragged edge / unaligned rows: scalar path
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    epilogue_scalar(p, drop, __uint_as_float(raw[j]), nc + j, z, row, obase, pbase);
-                continue;
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(raw[4 * g]), "r"(raw[4 * g + 1]),
+                             "r"(raw[4 * g + 2]), "r"(raw[4 * g + 3])
+                             : "memory");
             }
-            // each feature is a separate uniform branch around a 32-wide register loop, so only the code of
-            // the features in use is ever fetched (a per-element branch ladder thrashed the I-cache)
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(raw[j]);
-            if (p.bias) {
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = __ldg(b4 + j);
-                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            __syncwarp();
+            const int n = nc + 4 * cg;
+            const bool quad_ok = vec_ok && (n + 3 < p.N);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && quad_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+                const int r = (lane >> 3) + 4 * i;
+                const int row = m0 + q * 32 + r;
+                float4 v;
+                {
+                    const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((cg ^ (r & 7)) * 16);
+                    uint32_t x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                    v = make_float4(__uint_as_float(x0), __uint_as_float(x1), __uint_as_float(x2), __uint_as_float(x3));
+                }
+                if (row >= p.M || n >= p.N) continue;
+                const long long ob = obatch + (long long)row * p.ld_out + n;
+                const long long pb = pbatch + (long long)row * p.ld_pl + n;
+                if (!quad_ok) {                              // ragged edge / unaligned leading dimension
+                    epilogue_scalar(p, drop, v.x, n, z, row, ob - n, pb - n);
+                    epilogue_scalar(p, drop, v.y, n + 1, z, row, ob - n, pb - n);
+                    epilogue_scalar(p, drop, v.z, n + 2, z, row, ob - n, pb - n);
+                    epilogue_scalar(p, drop, v.w, n + 3, z, row, ob - n, pb - n);
+                    continue;
+                }
+                v.x = p.alpha * v.x + bias4.x; v.y = p.alpha * v.y + bias4.y;
+                v.z = p.alpha * v.z + bias4.z; v.w = p.alpha * v.w + bias4.w;
+                if (p.aux_out) *reinterpret_cast<float4*>(p.aux_out + ob) = v;
+                if (p.act == YV_ACT_GELU) {
+                    v.x = yv_gelu(v.x); v.y = yv_gelu(v.y); v.z = yv_gelu(v.z); v.w = yv_gelu(v.w);
+                } else if (p.act == YV_ACT_RELU) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                if (drop.thresh) {
+                    const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
+                    v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
+                    v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
+                }
+                if (p.act == YV_ACT_MUL_GELU_GRAD) {
+                    const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
+                    v.x *= yv_gelu_grad(t.x); v.y *= yv_gelu_grad(t.y); v.z *= yv_gelu_grad(t.z); v.w *= yv_gelu_grad(t.w);
+                } else if (p.act == YV_ACT_MUL_RELU_MASK) {
+                    const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
+                    v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
+                    v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+                }
+                if (p.residual) {
+                    const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
+                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                }
+                if (p.out32) *reinterpret_cast<float4*>(p.out32 + ob) = v;
+                if (p.out_planes) {
+                    __align__(8) __nv_bfloat16 h4[4], l4[4];
+                    yv_split(v.x, h4[0], l4[0]); yv_split(v.y, h4[1], l4[1]);
+                    yv_split(v.z, h4[2], l4[2]); yv_split(v.w, h4[3], l4[3]);
+                    *reinterpret_cast<uint2*>(p.out_planes + pb) = *reinterpret_cast<uint2*>(h4);
+                    *reinterpret_cast<uint2*>(p.out_planes + pb + p.pl_plane_stride) = *reinterpret_cast<uint2*>(l4);
                 }
             }
-            if (p.aux_out) {
-                float4* o = reinterpret_cast<float4*>(p.aux_out + obase + nc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.act == YV_ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = yv_gelu(v[j]);
-            } else if (p.act == YV_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (drop.thresh) {
-                const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + nc);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= yv_drop_mul(drop, i0 + j);
-            }
-            if (p.act == YV_ACT_MUL_GELU_GRAD || p.act == YV_ACT_MUL_RELU_MASK) {
-                const float4* a4 = reinterpret_cast<const float4*>(p.aux_in + obase + nc);
-                const bool gelu = p.act == YV_ACT_MUL_GELU_GRAD;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = a4[j];
-                    if (gelu) {
-                        v[4 * j] *= yv_gelu_grad(t.x); v[4 * j + 1] *= yv_gelu_grad(t.y);
-                        v[4 * j + 2] *= yv_gelu_grad(t.z); v[4 * j + 3] *= yv_gelu_grad(t.w);
-                    } else {
-                        v[4 * j] = t.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = t.y > 0.f ? v[4 * j + 1] : 0.f;
-                        v[4 * j + 2] = t.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = t.w > 0.f ? v[4 * j + 3] : 0.f;
-                    }
-                }
-            }
-            if (p.residual) {
-                const float4* r4 = reinterpret_cast<const float4*>(p.residual + obase + nc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = r4[j];
-                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-                }
-            }
-            if (p.out32) {
-                float4* o = reinterpret_cast<float4*>(p.out32 + obase + nc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.out_planes) {
-                __nv_bfloat16* hi = p.out_planes + pbase + nc;
-                __nv_bfloat16* lo = hi + p.pl_plane_stride;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __align__(16) __nv_bfloat16 h8[8], l8[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) yv_split(v[8 * j + t], h8[t], l8[t]);
-                    reinterpret_cast<uint4*>(hi)[j] = *reinterpret_cast<uint4*>(h8);
-                    reinterpret_cast<uint4*>(lo)[j] = *reinterpret_cast<uint4*>(l8);
-                }
-            }
+            __syncwarp();                                    // staging buffer is reused by the next chunk
         }
     }
 
