@@ -44,6 +44,14 @@ def _cuda_ops(t: torch.Tensor):
     return _ops
 
 
+def _share(t: torch.Tensor, stream):
+    """A tensor produced on a branch stream is consumed on ``stream`` from now on (allocator bookkeeping)."""
+    t.record_stream(stream)
+    tag = getattr(t, "_yv_planes", None)
+    if tag is not None:
+        tag[0].keep.record_stream(stream)
+
+
 def gelu(x):
     """erf-form GELU (reference :113-119)."""
     return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -434,6 +442,23 @@ class BertConnectionLayer(nn.Module):
         ctx_t, ctx_v, probs = self.biattention(input_tensor1, attention_mask1, input_tensor2, attention_mask2,
                                                co_attention_mask, use_co_attention_mask)
         # ctx_v (vision queries over text) updates the vision stream, ctx_t the text stream (reference :671)
+        if input_tensor1.is_cuda and _cuda_ops(input_tensor1).rt(input_tensor1.device).concurrent:
+            # the two streams are independent after the bi-attention: vision half on the branch stream
+            bo = self.biOutput
+            ops, r = _ops, _ops.rt(input_tensor1.device)
+            cur = torch.cuda.current_stream(input_tensor1.device)
+            side = r.branch_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                a1 = ops.dense_res_ln(ctx_v, input_tensor1, bo.dense1.weight, bo.dense1.bias, bo.LayerNorm1.weight,
+                                      bo.LayerNorm1.bias, bo.dropout1.p if self.training else 0.0, bo._site1)
+                o1 = self.v_output(self.v_intermediate(a1), a1)
+            a2 = ops.dense_res_ln(ctx_t, input_tensor2, bo.dense2.weight, bo.dense2.bias, bo.LayerNorm2.weight,
+                                  bo.LayerNorm2.bias, bo.dropout2.p if self.training else 0.0, bo._site2)
+            o2 = self.t_output(self.t_intermediate(a2), a2)
+            cur.wait_stream(side)
+            _share(o1, cur)
+            return o1, o2, probs
         a1, a2 = self.biOutput(ctx_v, input_tensor1, ctx_t, input_tensor2)
         o1 = self.v_output(self.v_intermediate(a1), a1)
         o2 = self.t_output(self.t_intermediate(a2), a2)
@@ -469,6 +494,25 @@ class BertEncoder(nn.Module):
                 sink.append(probs)
         return x
 
+    def _run_both(self, v_lo, v_hi, v_frozen, v, v_mask, v_sink, t_lo, t_hi, t_frozen, t, t_mask, t_sink, keep):
+        """Vision layers [v_lo, v_hi) and text layers [t_lo, t_hi) are independent between two connection layers
+        (reference :753-769): on CUDA the vision branch is issued on a second stream so both overlap (autograd
+        replays each branch's backward on the stream of its forward)."""
+        if v.is_cuda and v_hi > v_lo and t_hi > t_lo and _cuda_ops(v).rt(v.device).concurrent:
+            r = _ops.rt(v.device)
+            cur = torch.cuda.current_stream(v.device)
+            side = r.branch_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                v = self._run(self.v_layer, v_lo, v_hi, v_frozen, v, v_mask, keep, v_sink)
+            t = self._run(self.layer, t_lo, t_hi, t_frozen, t, t_mask, keep, t_sink)
+            cur.wait_stream(side)
+            _share(v, cur)
+            return v, t
+        v = self._run(self.v_layer, v_lo, v_hi, v_frozen, v, v_mask, keep, v_sink)
+        t = self._run(self.layer, t_lo, t_hi, t_frozen, t, t_mask, keep, t_sink)
+        return v, t
+
     def forward(self, txt_embedding, image_embedding, txt_attention_mask, image_attention_mask,
                 co_attention_mask=None, output_all_encoded_layers=True, output_all_attention_masks=False):
         v_start = t_start = 0
@@ -480,10 +524,10 @@ class BertEncoder(nn.Module):
         for count, (v_end, t_end) in enumerate(zip(self.v_biattention_id, self.t_biattention_id)):
             assert self.fixed_t_layer <= t_end
             assert self.fixed_v_layer <= v_end
-            image_embedding = self._run(self.v_layer, v_start, v_end, self.fixed_v_layer, image_embedding,
-                                        image_attention_mask, output_all_attention_masks, att_v)
-            txt_embedding = self._run(self.layer, t_start, t_end, self.fixed_t_layer, txt_embedding,
-                                      txt_attention_mask, output_all_attention_masks, att_t)
+            image_embedding, txt_embedding = self._run_both(
+                v_start, v_end, self.fixed_v_layer, image_embedding, image_attention_mask, att_v,
+                t_start, t_end, self.fixed_t_layer, txt_embedding, txt_attention_mask, att_t,
+                output_all_attention_masks)
             if count == 0 and self.in_batch_pairs:
                 # every text against every image of the batch: batch becomes n*n (reference :771-778)
                 image_embedding = image_embedding.unsqueeze(0).expand(n, n, num_regions, v_hidden) \
@@ -511,10 +555,9 @@ class BertEncoder(nn.Module):
             if output_all_encoded_layers:
                 all_t.append(txt_embedding)
                 all_v.append(image_embedding)
-        image_embedding = self._run(self.v_layer, v_start, len(self.v_layer), 0, image_embedding,
-                                    image_attention_mask, output_all_attention_masks, att_v)
-        txt_embedding = self._run(self.layer, t_start, len(self.layer), 0, txt_embedding, txt_attention_mask,
-                                  output_all_attention_masks, att_t)
+        image_embedding, txt_embedding = self._run_both(
+            v_start, len(self.v_layer), 0, image_embedding, image_attention_mask, att_v,
+            t_start, len(self.layer), 0, txt_embedding, txt_attention_mask, att_t, output_all_attention_masks)
         if not output_all_encoded_layers:
             all_t.append(txt_embedding)
             all_v.append(image_embedding)
@@ -647,10 +690,21 @@ class BertPreTrainingHeads(nn.Module):
             pooled = self.dropout(pooled_output_t * pooled_output_v)
         else:
             assert False
-        scores_t = self.predictions(sequence_output_t)
         # [N, 2] next-sentence-style score: a [N,1024]x[1024,2] product, left to ATen (not a hot-path op;
         # Lily discards it, lily.py:87)
         rel = self.bi_seq_relationship(pooled)
+        if sequence_output_t.is_cuda and _cuda_ops(sequence_output_t).rt(sequence_output_t.device).concurrent:
+            r = _ops.rt(sequence_output_t.device)
+            cur = torch.cuda.current_stream(sequence_output_t.device)
+            side = r.branch_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                scores_v = self.imagePredictions(sequence_output_v)
+            scores_t = self.predictions(sequence_output_t)
+            cur.wait_stream(side)
+            _share(scores_v, cur)
+            return scores_t, scores_v, rel
+        scores_t = self.predictions(sequence_output_t)
         scores_v = self.imagePredictions(sequence_output_v)
         return scores_t, scores_v, rel
 

@@ -52,6 +52,19 @@ class Runtime:
         seed = int(os.environ.get("YVB200_SEED", "20231117"))
         self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
         self.arena = WeightArena(device)
+        # independent work (dgrad vs wgrad, text vs vision stream) is issued on helper CUDA streams so that the
+        # captured step graph has parallel branches; YVB200_CONCURRENT=0 serialises everything on one stream
+        self.concurrent = os.environ.get("YVB200_CONCURRENT", "1") != "0"
+        self._helpers: Dict[int, torch.cuda.Stream] = {}
+        self.branch_stream = torch.cuda.Stream(device=device)
+
+    def helper(self) -> torch.cuda.Stream:
+        """The helper stream paired with the current stream (created on first use)."""
+        cur = torch.cuda.current_stream(self.device)
+        h = self._helpers.get(cur.cuda_stream)
+        if h is None:
+            h = self._helpers[cur.cuda_stream] = torch.cuda.Stream(device=self.device)
+        return h
 
     def set_precision(self, mode: str):
         self.passes = 3 if mode == "bf16x3" else 1
@@ -222,11 +235,24 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
     dx = dW = db = None
     if need_dx:
         dx = _f32(M, K, device=device)
-        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
     if need_dw:
         dW = _f32(N, K, device=device)
-        L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
         db = _f32(N, device=device)
+    fork = r.concurrent and need_dx and need_dw
+    if fork:                                    # wgrad + bias grad on the helper stream, dgrad on this one
+        cur = torch.cuda.current_stream(device)
+        side = r.helper()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
+            L.colsum_planes(dp, db)
+        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
+        cur.wait_stream(side)
+        return dx, dW, db
+    if need_dx:
+        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
+    if need_dw:
+        L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
         L.colsum_planes(dp, db)
     return dx, dW, db
 
@@ -528,10 +554,7 @@ class BiAttentionFn(Function):
         w2 = r.arena.get((Wq2, Wk2, Wv2))
         qkv1 = Planes.empty(Mv, 3 * H, dev)
         qkv2 = Planes.empty(Mt, 3 * H, dev)
-        L.gemm(Mv, 3 * H, Kv, L.op_of(xvp), L.op_of(w1), passes=r.passes, bias=_cat_bias((bq1, bk1, bv1)),
-               out_planes=qkv1.ptr(), ld_pl=qkv1.ld, pl_plane_stride=qkv1.plane_stride)
-        L.gemm(Mt, 3 * H, Kt, L.op_of(xtp), L.op_of(w2), passes=r.passes, bias=_cat_bias((bq2, bk2, bv2)),
-               out_planes=qkv2.ptr(), ld_pl=qkv2.ld, pl_plane_stride=qkv2.plane_stride)
+        b1c, b2c = _cat_bias((bq1, bk1, bv1)), _cat_bias((bq2, bk2, bv2))
         vm, tm = _mask2d(vmask, pairs, V), _mask2d(tmask, pairs, T)
         c1 = _f32(Mt, H, device=dev)
         c1p = Planes.empty(Mt, H, dev)
@@ -539,8 +562,22 @@ class BiAttentionFn(Function):
         c2p = Planes.empty(Mv, H, dev)
         q1, k1, v1 = HeadView(qkv1, 0, V), HeadView(qkv1, H, V), HeadView(qkv1, 2 * H, V)
         q2, k2, v2 = HeadView(qkv2, 0, T), HeadView(qkv2, H, T), HeadView(qkv2, 2 * H, T)
-        P1, P1p = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
+        cur = torch.cuda.current_stream(dev)
+        side = r.helper() if r.concurrent else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            L.gemm(Mt, 3 * H, Kt, L.op_of(xtp), L.op_of(w2), passes=r.passes, bias=b2c,
+                   out_planes=qkv2.ptr(), ld_pl=qkv2.ld, pl_plane_stride=qkv2.plane_stride)
+        L.gemm(Mv, 3 * H, Kv, L.op_of(xvp), L.op_of(w1), passes=r.passes, bias=b1c,
+               out_planes=qkv1.ptr(), ld_pl=qkv1.ld, pl_plane_stride=qkv1.plane_stride)
+        cur.wait_stream(side)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            P1, P1p = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
         P2, P2p = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2)
+        cur.wait_stream(side)
+        for t_ in (P1, P1p.keep):
+            t_.record_stream(cur)
         ctx.r, ctx.spec = r, spec
         ctx.keep = (xvp, xtp, w1, w2, qkv1, qkv2, P1p, P2p)
         ctx.dims = (pairs, V, T, Kv, Kt, H, heads, dh)
@@ -565,8 +602,13 @@ class BiAttentionFn(Function):
         q2, k2, v2 = HeadView(qkv2, 0, T), HeadView(qkv2, H, T), HeadView(qkv2, 2 * H, T)
         dq1, dk1, dv1 = HeadView(d1, 0, V), HeadView(d1, H, V), HeadView(d1, 2 * H, V)
         dq2, dk2, dv2 = HeadView(d2, 0, T), HeadView(d2, H, T), HeadView(d2, 2 * H, T)
-        _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
+        cur = torch.cuda.current_stream(dev)
+        side = r.helper() if r.concurrent else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
         _attn_bwd(r, dO2, q1, k2, v2, P2, P2p, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2)
+        cur.wait_stream(side)
         dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True)
         dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True)
         return ((dxv.view(pairs, V, Kv) if dxv is not None else None), None,
