@@ -3,7 +3,9 @@
 //   D[z] = epilogue(alpha * sum_p A_p[z] . B_p[z]^T)        p in {(hi,hi)} or {(hi,hi),(hi,lo),(lo,hi)}
 //
 // One CTA per 128x128 output tile, 192 threads:
-//   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d with 128B swizzle into a 3/6-stage ring
+//   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d (swizzled) into a 3/6-stage, 96 KB ring
+//              (128x128x32 tiles keep the CTA under half an SM's shared memory: two CTAs co-reside, so one
+//               CTA's prologue / epilogue overlaps the other's MMA main loop)
 //   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), commits to mbarriers
 //   warps 2-9: epilogue -- tcgen05.ld 32x32 chunks, transposed through swizzled smem for coalesced I/O
 // Operands may be K-major or MN-major (transposed views): dgrad / wgrad / attention products need no
@@ -13,6 +15,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/yvb200.h"
@@ -22,9 +25,14 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
-constexpr int BLOCK_K = 64;                                   // 64 bf16 = 128 B = one swizzle row
+#ifndef YV_BLOCK_K
+#define YV_BLOCK_K 32
+#endif
+constexpr int BLOCK_K = YV_BLOCK_K;                           // 32: 64 B rows / 64B swizzle / 2 CTAs per SM; 64: 128B swizzle
+constexpr int KMAJ_LAYOUT = BLOCK_K == 32 ? 4 : 2;            // UMMA layout type of K-major tiles (SWIZZLE_64B / _128B)
+constexpr int KMAJ_SBO = BLOCK_K * 2 * 8;                     // 8 rows of BLOCK_K bf16
 constexpr int UMMA_K = 16;
-constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 16 KB (A and B tiles have the same size)
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 8 KB (A and B tiles have the same size)
 constexpr int NUM_THREADS = 320;                               // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 128;
 
@@ -32,13 +40,15 @@ template <int PASSES>
 struct Cfg {
     static constexpr int TILES_PER_STAGE = PASSES == 3 ? 4 : 2;   // A_hi, B_hi, (A_lo, B_lo)
     static constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
-    static constexpr int STAGES = PASSES == 3 ? 3 : 6;
+    static constexpr int STAGES = PASSES == 3 ? 3 : 6;            // 96 KB (BLOCK_K=32) / 192 KB (64) operand ring
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(STAGES * STAGE_BYTES >= 8 * 4096, "epilogue staging (8 warps x 4 KB) reuses the operand ring");
 };
 
 struct KParams {
     int M, N, K;
     int nb0;
+    int splits, kb_per_split;   // split-K (only for un-batched launches with a linear, f32-only epilogue)
     int a_mn, b_mn;
     float alpha;
     int act;
@@ -112,16 +122,16 @@ YV_DEVINL void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle
-//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused
-//   MN-major: 64-element chunks along M/N are LBO bytes apart, 8-k-row groups 1024 B apart (SBO)
-YV_DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (sm_100 "version 1")
+//   K-major  (64B swizzle) : rows of 64 B, 8-row groups 512 B apart (SBO); LBO unused
+//   MN-major (128B swizzle): 64-element chunks along M/N are LBO bytes apart, 8-k-row groups 1024 B apart (SBO)
+YV_DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
+    d |= (uint64_t)layout << 61;   // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
     return d;
 }
 
@@ -156,7 +166,7 @@ __device__ long long yv_dbg[32];
 
 // ------------------------------------------------------------------------------------------- kernel
 template <int PASSES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, BLOCK_K == 32 ? 2 : 1)
 yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const KParams p) {
     using C = Cfg<PASSES>;
@@ -175,9 +185,12 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BLOCK_M;
     const int n0 = blockIdx.x * BLOCK_N;
-    const int z = blockIdx.z;
+    const int split = blockIdx.z % p.splits;
+    const int z = blockIdx.z / p.splits;
     const int b0 = z % p.nb0, b1 = z / p.nb0;
-    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_lo = split * p.kb_per_split;
+    const int num_kb = min(p.kb_per_split, total_kb - kb_lo);   // >= 1 by construction on the host
     if (threadIdx.x == 0) YV_T(0);
 
     if (threadIdx.x == 0) {
@@ -211,7 +224,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
                 mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                const int k0 = kb * BLOCK_K;
+                const int k0 = (kb_lo + kb) * BLOCK_K;
 #pragma unroll
                 for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
                     const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
@@ -257,8 +270,8 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
                     const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
                     const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
-                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024) : make_desc(sa, 16, 1024);
-                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024) : make_desc(sb, 16, 1024);
+                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, KMAJ_LAYOUT);
+                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, KMAJ_LAYOUT);
                 }
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -319,7 +332,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int n = nc + 4 * cg;
             const bool quad_ok = vec_ok && (n + 3 < p.N);
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && quad_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            if (p.bias && quad_ok && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll 2
             for (int i = 0; i < 8; ++i) {
                 const int r = (lane >> 3) + 4 * i;
@@ -343,6 +356,23 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 v.x = p.alpha * v.x + bias4.x; v.y = p.alpha * v.y + bias4.y;
                 v.z = p.alpha * v.z + bias4.z; v.w = p.alpha * v.w + bias4.w;
+                if (p.splits > 1) {
+                    // split-K: partial sums meet in a zero-initialised f32 output through vector reductions; the
+                    // epilogue is linear here (bias and residual come from split 0, dropout scales every partial)
+                    if (drop.thresh) {
+                        const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
+                        v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
+                        v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
+                    }
+                    if (p.residual && split == 0) {
+                        const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out32 + ob), "f"(v.x), "f"(v.y),
+                                 "f"(v.z), "f"(v.w)
+                                 : "memory");
+                    continue;
+                }
                 if (p.aux_out) *reinterpret_cast<float4*>(p.aux_out + ob) = v;
                 if (p.act == YV_ACT_GELU) {
                     v.x = yv_gelu(v.x); v.y = yv_gelu(v.y); v.z = yv_gelu(v.z); v.w = yv_gelu(v.w);
@@ -391,6 +421,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 // ------------------------------------------------------------------------------------------- host
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
 
 int get_encode() {
     if (g_encode) return 0;
@@ -422,10 +453,12 @@ int make_map(CUtensorMap* map, const YvOperand& o, int passes, const char* which
     const cuuint64_t row_b = (cuuint64_t)o.ld * 2;
     cuuint64_t strides[4] = {row_b, o.nb0 > 1 ? (cuuint64_t)o.sb0 * 2 : row_b, o.nb1 > 1 ? (cuuint64_t)o.sb1 * 2 : row_b,
                              nplanes > 1 ? (cuuint64_t)o.plane_stride * 2 : row_b};
-    cuuint32_t box[5] = {64, (cuuint32_t)(o.mn_major ? BLOCK_K : BLOCK_M), 1, 1, 1};
+    // K-major: 32 k-elements (64 B, 64B swizzle) x 128 rows; MN-major: 64 m/n-elements (128 B, 128B swizzle) x 32 k-rows
+    cuuint32_t box[5] = {(cuuint32_t)(o.mn_major ? 64 : BLOCK_K), (cuuint32_t)(o.mn_major ? BLOCK_K : BLOCK_M), 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(o.ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, (o.mn_major || BLOCK_K == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YV_CHECK(r == CUDA_SUCCESS, "yv_gemm: cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", which,
              (int)r, (long long)o.inner, (long long)o.rows, (long long)o.ld);
@@ -475,9 +508,30 @@ extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
     YV_CHECK((g->act != YV_ACT_MUL_GELU_GRAD && g->act != YV_ACT_MUL_RELU_MASK) || g->aux_in,
              "yv_gemm: act %d needs aux_in", g->act);
 
-    dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, (unsigned)(a.nb0 * a.nb1));
+    const int tiles = ((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M);
+    const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
+    p.splits = 1;
+    p.kb_per_split = total_kb;
+    // split-K when the tile count leaves most SMs idle and the epilogue is linear with a plain f32 output whose
+    // rows are 16-byte aligned (the output must then be zero-filled: done here with a memset node)
+    const bool linear_epi = g->act == YV_ACT_NONE && !g->aux_out && !g->out_planes && g->out32 &&
+                            (g->ld_out % 4 == 0) && (g->N % 4 == 0) && (((uintptr_t)g->out32) & 15) == 0 &&
+                            (!g->residual || g->residual != g->out32) && (!g->bias || (((uintptr_t)g->bias) & 15) == 0) &&
+                            (!g->residual || (((uintptr_t)g->residual) & 15) == 0);
+    if (a.nb0 * a.nb1 == 1 && linear_epi && tiles * 2 <= 148 && total_kb >= 8 && g_split_k) {
+        int s = 148 / tiles;
+        if (s > total_kb / 4) s = total_kb / 4;
+        if (s > 16) s = 16;
+        if (s >= 2) {
+            p.kb_per_split = (total_kb + s - 1) / s;
+            p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+        }
+    }
+    dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, (unsigned)(a.nb0 * a.nb1 * p.splits));
     YV_CHECK(grid.y <= 65535 && grid.z <= 65535, "yv_gemm: grid too large");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p.splits > 1)
+        YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
     static bool attr_set = false;
     if (!attr_set) {
         YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
