@@ -90,7 +90,9 @@ int yv_rng_advance(uint64_t* rng, yv_stream_t stream);
  * dropout (embeddings: :254-255, :1367-1368).  y32 and/or y_planes may be NULL.  stats = {mean, rstd}[M].
  * bwd: dx = LN'(dy) (+ dx_add), dgamma/dbeta accumulated with atomics into zero-initialised buffers.
  *      dx_planes (optional) = dx * dropmask(pre_site): the operand of the preceding dense layer's
- *      dgrad/wgrad when that layer's output went through dropout before the residual add (:323-324).
+ *      dgrad/wgrad when that layer's output went through dropout before the residual add (:323-324);
+ *      dbias (optional, zero-initialised) accumulates the column sums of that same masked gradient, i.e.
+ *      the bias gradient of the preceding dense layer.
  * ---------------------------------------------------------------------------------------------- */
 int yv_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y32,
                      void* y_planes, int64_t plane_stride, float* stats, int64_t M, int32_t C, float drop_p,
@@ -98,7 +100,8 @@ int yv_layernorm_fwd(const float* x, const float* gamma, const float* beta, floa
 int yv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats,
                      float post_drop_p, uint32_t post_drop_site, const float* dx_add, float* dx32,
                      void* dx_planes, int64_t plane_stride, float pre_drop_p, uint32_t pre_drop_site,
-                     const uint64_t* rng, float* dgamma, float* dbeta, int64_t M, int32_t C, yv_stream_t stream);
+                     const uint64_t* rng, float* dgamma, float* dbeta, float* dbias, int64_t M, int32_t C,
+                     yv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * attention softmax (vilbert/vilbert.py:295-304, 424-433, 578-589, 598-611):
@@ -138,7 +141,8 @@ int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_stride, int64
 /* backward of the GEMM-epilogue activations when the upstream gradient arrives as f32:
  * planes = dy * act'(aux)  (GELU: aux = saved pre-activation, vilbert/vilbert.py:113-119; ReLU: aux = output) */
 int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux, int64_t ld_aux, int32_t act, void* planes,
-                     int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, yv_stream_t stream);
+                     int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, float* dbias /* optional column
+                     sums = bias gradient, zeroed by the call */, yv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fused losses (utils/utils_init.py:117-135)

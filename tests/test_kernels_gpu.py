@@ -162,10 +162,12 @@ def test_layernorm_fwd_bwd(L):
     dxp = L.Planes.empty(M, Cd, "cuda")
     dg = torch.zeros(Cd, device="cuda")
     db = torch.zeros(Cd, device="cuda")
-    L.layernorm_bwd(dy, x.detach(), g.detach(), st, dx, dxp, dg, db, M, Cd)
+    dbias = torch.zeros(Cd, device="cuda")
+    L.layernorm_bwd(dy, x.detach(), g.detach(), st, dx, dxp, dg, db, M, Cd, dbias=dbias)
     torch.cuda.synchronize()
     assert _rel(dx, x.grad) < 1e-5 and _rel(dxp.float(), x.grad) < 2e-5
     assert _rel(dg, g.grad) < 1e-5 and _rel(db, b.grad) < 1e-5
+    assert _rel(dbias, x.grad.sum(0)) < 1e-4
 
 
 def test_softmax_fwd_bwd(L):

@@ -105,78 +105,100 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
 }
 
-// grid-stride over rows; per-lane register accumulators for dgamma/dbeta (C <= 32*MAXPL)
-template <int MAXPL>
-__global__ void __launch_bounds__(THREADS)
+// Thread t owns columns [4t, 4t+4); a block walks the rows four at a time (grid-stride).  Row statistics need a
+// block reduction (shuffle + one smem exchange per 4 rows); dgamma / dbeta / dbias live in 12 registers per thread
+// and leave through one vector reduction per thread at the end.
+constexpr int LNB_ROWS = 4;
+__global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ stats, float post_p, unsigned post_site, const float* __restrict__ dx_add,
                      float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxp, long long plane_stride, float pre_p,
                      unsigned pre_site, const unsigned long long* rng, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, long long M, int C) {
-    __shared__ float red[WARPS][32 * MAXPL + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                     float* __restrict__ dbeta, float* __restrict__ dbias, long long M, int C) {
+    __shared__ float red[8][2 * LNB_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int c0 = tid * 4;
+    const bool active = c0 < C;
     const YvDrop dpost = yv_drop_make(rng, post_site, post_p);
     const YvDrop dpre = yv_drop_make(rng, pre_site, pre_p);
-    float ag[MAXPL], ab[MAXPL];
+    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) gm = *reinterpret_cast<const float4*>(gamma + c0);
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, abias[4] = {0.f, 0.f, 0.f, 0.f};
+    const float invC = 1.f / C;
+    for (long long row0 = blockIdx.x * (long long)LNB_ROWS; row0 < M; row0 += (long long)gridDim.x * LNB_ROWS) {
+        float g[LNB_ROWS][4], xh[LNB_ROWS][4], part[2 * LNB_ROWS], rs[LNB_ROWS];
 #pragma unroll
-    for (int i = 0; i < MAXPL; ++i) ag[i] = ab[i] = 0.f;
-    for (long long row = blockIdx.x * (long long)WARPS + warp; row < M; row += (long long)gridDim.x * WARPS) {
-        const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-        const float* xr = x + row * C;
-        const float* dyr = dy + row * C;
-        float g[MAXPL], xh[MAXPL];
-        float s1 = 0.f, s2 = 0.f;
+        for (int r = 0; r < LNB_ROWS; ++r) {
+            const long long row = row0 + r;
+            part[2 * r] = part[2 * r + 1] = 0.f;
+            rs[r] = 0.f;
 #pragma unroll
-        for (int i = 0; i < MAXPL; ++i) {
-            const int c = lane + 32 * i;
-            g[i] = 0.f; xh[i] = 0.f;
-            if (c < C) {
-                float d = dyr[c];
-                if (dpost.thresh) d *= yv_drop_mul(dpost, (uint32_t)(row * C + c));
-                xh[i] = (xr[c] - mean) * rstd;
-                ag[i] += d * xh[i];
-                ab[i] += d;
-                g[i] = d * gamma[c];
-                s1 += g[i];
-                s2 += g[i] * xh[i];
-            }
-        }
-        s1 = yv_warp_sum(s1) / C;
-        s2 = yv_warp_sum(s2) / C;
+            for (int j = 0; j < 4; ++j) g[r][j] = xh[r][j] = 0.f;
+            if (active && row < M) {
+                const float mean = stats[2 * row];
+                rs[r] = stats[2 * row + 1];
+                const float4 d4 = *reinterpret_cast<const float4*>(dy + row * C + c0);
+                const float4 x4 = *reinterpret_cast<const float4*>(x + row * C + c0);
+                float d[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+                const float gv[4] = {gm.x, gm.y, gm.z, gm.w};
 #pragma unroll
-        for (int i = 0; i < MAXPL; ++i) {
-            const int c = lane + 32 * i;
-            if (c < C) {
-                float d = rstd * (g[i] - s1 - xh[i] * s2);
-                if (dx_add) d += dx_add[row * C + c];
-                if (dx32) dx32[row * C + c] = d;
-                if (dxp) {
-                    float dd = d;
-                    if (dpre.thresh) dd *= yv_drop_mul(dpre, (uint32_t)(row * C + c));
-                    __nv_bfloat16 h, l;
-                    yv_split(dd, h, l);
-                    dxp[row * C + c] = h;
-                    dxp[plane_stride + row * C + c] = l;
+                for (int j = 0; j < 4; ++j) {
+                    if (dpost.thresh) d[j] *= yv_drop_mul(dpost, (uint32_t)(row * C + c0 + j));
+                    xh[r][j] = (xv[j] - mean) * rs[r];
+                    ag[j] += d[j] * xh[r][j];
+                    ab[j] += d[j];
+                    g[r][j] = d[j] * gv[j];
+                    part[2 * r] += g[r][j];
+                    part[2 * r + 1] += g[r][j] * xh[r][j];
                 }
             }
         }
-    }
-    if (dgamma == nullptr && dbeta == nullptr) return;
-    // block reduction of the per-warp partial sums, then one atomic per column per block
-    for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int i = 0; i < MAXPL; ++i) red[warp][lane + 32 * i] = pass == 0 ? ag[i] : ab[i];
+        for (int i = 0; i < 2 * LNB_ROWS; ++i) part[i] = yv_warp_sum(part[i]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 2 * LNB_ROWS; ++i) red[warp][i] = part[i];
+        }
         __syncthreads();
-        float* dst = pass == 0 ? dgamma : dbeta;
-        if (dst)
-            for (int c = threadIdx.x; c < C; c += THREADS) {
-                float t = 0.f;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) t += red[w][c];
-                atomicAdd(dst + c, t);
+        for (int i = 0; i < 2 * LNB_ROWS; ++i) {
+            float t = 0.f;
+            for (int w = 0; w < nwarps; ++w) t += red[w][i];
+            part[i] = t * invC;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < LNB_ROWS; ++r) {
+            const long long row = row0 + r;
+            if (!(active && row < M)) continue;
+            float o[4], om[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = rs[r] * (g[r][j] - part[2 * r] - xh[r][j] * part[2 * r + 1]);
+            if (dx_add) {
+                const float4 a4 = *reinterpret_cast<const float4*>(dx_add + row * C + c0);
+                o[0] += a4.x; o[1] += a4.y; o[2] += a4.z; o[3] += a4.w;
             }
-        __syncthreads();
+            if (dx32) *reinterpret_cast<float4*>(dx32 + row * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                om[j] = o[j];
+                if (dpre.thresh) om[j] *= yv_drop_mul(dpre, (uint32_t)(row * C + c0 + j));
+                abias[j] += om[j];
+            }
+            if (dxp) {
+                __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yv_split(om[j], h4[j], l4[j]);
+                *reinterpret_cast<uint2*>(dxp + row * C + c0) = *reinterpret_cast<uint2*>(h4);
+                *reinterpret_cast<uint2*>(dxp + plane_stride + row * C + c0) = *reinterpret_cast<uint2*>(l4);
+            }
+        }
     }
+    if (!active) return;
+    if (dgamma) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + c0), "f"(ag[0]), "f"(ag[1]), "f"(ag[2]), "f"(ag[3]) : "memory");
+    if (dbeta) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + c0), "f"(ab[0]), "f"(ab[1]), "f"(ab[2]), "f"(ab[3]) : "memory");
+    if (dbias) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + c0), "f"(abias[0]), "f"(abias[1]), "f"(abias[2]), "f"(abias[3]) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,35 +365,92 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, long lo
     atomicAdd(out + c, s);
 }
 
-// planes variant: x = hi + lo
-__global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long plane_stride, long long rows,
-                                     int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    const long long r0 = blockIdx.y * (long long)CS_ROWS;
-    const long long r1 = min(rows, r0 + CS_ROWS);
-    float s = 0.f;
-    for (long long r = r0; r < r1; ++r)
-        s += __bfloat162float(x[r * ld + c]) + __bfloat162float(x[plane_stride + r * ld + c]);
-    atomicAdd(out + c, s);
+// planes variant: x = hi + lo.  Thread owns 8 columns (one 16-byte load per plane per row), a block covers
+// 1024 columns x CSP_ROWS rows; partial sums leave through vector reductions.
+constexpr int CSP_ROWS = 32;
+__global__ void __launch_bounds__(128)
+colsum_planes_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long plane_stride, long long rows, int cols,
+                     float* __restrict__ out) {
+    const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (c0 >= cols) return;
+    const long long r0 = blockIdx.y * (long long)CSP_ROWS;
+    const long long r1 = min(rows, r0 + CSP_ROWS);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 + 8 <= cols && (ld & 7) == 0 && (plane_stride & 7) == 0) {
+#pragma unroll 4
+        for (long long r = r0; r < r1; ++r) {
+            const uint4 h = *reinterpret_cast<const uint4*>(x + r * ld + c0);
+            const uint4 l = *reinterpret_cast<const uint4*>(x + plane_stride + r * ld + c0);
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+            const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = __bfloat1622float2(hp[j]), b = __bfloat1622float2(lp[j]);
+                acc[2 * j] += a.x + b.x;
+                acc[2 * j + 1] += a.y + b.y;
+            }
+        }
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+    } else {
+        for (int j = 0; j < 8 && c0 + j < cols; ++j) {
+            float t = 0.f;
+            for (long long r = r0; r < r1; ++r)
+                t += __bfloat162float(x[r * ld + c0 + j]) + __bfloat162float(x[plane_stride + r * ld + c0 + j]);
+            atomicAdd(out + c0 + j, t);
+        }
+    }
 }
 
-// dpre = dy * act'(aux) -> planes   (GELU: aux = pre-activation; ReLU: aux = forward output)
-__global__ void act_bwd_split_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ aux,
-                                     long long ld_aux, int act, __nv_bfloat16* __restrict__ dst, long long ld_dst,
-                                     long long plane_stride, long long rows, long long cols) {
-    const long long total = rows * cols;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / cols, c = i - r * cols;
-        float d = dy[r * ld_dy + c];
-        if (act == YV_ACT_GELU) d *= yv_gelu_grad(aux[r * ld_aux + c]);
-        else if (act == YV_ACT_RELU) d = aux[r * ld_aux + c] > 0.f ? d : 0.f;
-        __nv_bfloat16 h, l;
-        yv_split(d, h, l);
-        dst[r * ld_dst + c] = h;
-        dst[plane_stride + r * ld_dst + c] = l;
+// dpre = dy * act'(aux) -> planes   (GELU: aux = pre-activation; ReLU: aux = forward output); optional column sums
+// of dpre (the bias gradient).  Thread owns 4 columns, a block covers 1024 columns x ABS_ROWS rows.
+constexpr int ABS_ROWS = 16;
+__global__ void __launch_bounds__(256)
+act_bwd_split_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ aux, long long ld_aux, int act,
+                     __nv_bfloat16* __restrict__ dst, long long ld_dst, long long plane_stride, long long rows, long long cols,
+                     float* __restrict__ dbias) {
+    const long long c0 = (blockIdx.x * 256LL + threadIdx.x) * 4;
+    if (c0 >= cols) return;
+    const long long r0 = blockIdx.y * (long long)ABS_ROWS;
+    const long long r1 = min(rows, r0 + ABS_ROWS);
+    const bool vec = (c0 + 4 <= cols) && ((ld_dy & 3) == 0) && ((ld_aux & 3) == 0) && ((ld_dst & 3) == 0) &&
+                     ((plane_stride & 3) == 0) && ((((uintptr_t)dy | (uintptr_t)aux) & 15) == 0) && ((((uintptr_t)dst) & 7) == 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long r = r0; r < r1; ++r) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f}, a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dy + r * ld_dy + c0);
+            d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+            if (act != YV_ACT_NONE) {
+                const float4 a4 = *reinterpret_cast<const float4*>(aux + r * ld_aux + c0);
+                a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+            }
+        } else {
+            for (int j = 0; j < 4 && c0 + j < cols; ++j) {
+                d[j] = dy[r * ld_dy + c0 + j];
+                if (act != YV_ACT_NONE) a[j] = aux[r * ld_aux + c0 + j];
+            }
+        }
+        __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (act == YV_ACT_GELU) d[j] *= yv_gelu_grad(a[j]);
+            else if (act == YV_ACT_RELU) d[j] = a[j] > 0.f ? d[j] : 0.f;
+            acc[j] += d[j];
+            yv_split(d[j], h4[j], l4[j]);
+        }
+        if (vec) {
+            *reinterpret_cast<uint2*>(dst + r * ld_dst + c0) = *reinterpret_cast<uint2*>(h4);
+            *reinterpret_cast<uint2*>(dst + plane_stride + r * ld_dst + c0) = *reinterpret_cast<uint2*>(l4);
+        } else {
+            for (int j = 0; j < 4 && c0 + j < cols; ++j) {
+                dst[r * ld_dst + c0 + j] = h4[j];
+                dst[plane_stride + r * ld_dst + c0 + j] = l4[j];
+            }
+        }
     }
+    if (dbias)
+        for (int j = 0; j < 4 && c0 + j < cols; ++j) atomicAdd(dbias + c0 + j, acc[j]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -564,18 +643,19 @@ extern "C" int yv_layernorm_fwd(const float* x, const float* gamma, const float*
 extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, float post_drop_p,
                                 uint32_t post_drop_site, const float* dx_add, float* dx32, void* dx_planes,
                                 int64_t plane_stride, float pre_drop_p, uint32_t pre_drop_site, const uint64_t* rng,
-                                float* dgamma, float* dbeta, int64_t M, int32_t C, yv_stream_t stream) {
+                                float* dgamma, float* dbeta, float* dbias, int64_t M, int32_t C, yv_stream_t stream) {
     YV_CHECK(dy && x && gamma && stats && M > 0 && C > 0, "yv_layernorm_bwd: bad arguments");
-    YV_CHECK(C <= 1024, "yv_layernorm_bwd: hidden size %d > 1024 not supported", C);
-    const int grid = grid_for(M, WARPS, 148 * 2);
-    auto* rp = reinterpret_cast<const unsigned long long*>(rng);
-    auto* pl = reinterpret_cast<__nv_bfloat16*>(dx_planes);
-    if (C <= 128)
-        layernorm_bwd_kernel<4><<<grid, THREADS, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
-                                                                 pl, plane_stride, pre_drop_p, pre_drop_site, rp, dgamma, dbeta, M, C);
-    else
-        layernorm_bwd_kernel<32><<<grid, THREADS, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
-                                                                  pl, plane_stride, pre_drop_p, pre_drop_site, rp, dgamma, dbeta, M, C);
+    YV_CHECK(C <= 1024 && C % 4 == 0, "yv_layernorm_bwd: hidden size %d must be a multiple of 4 and <= 1024", C);
+    YV_CHECK(((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)gamma | (uintptr_t)dx_add | (uintptr_t)dx32 | (uintptr_t)dgamma |
+                (uintptr_t)dbeta | (uintptr_t)dbias) & 15) == 0) && ((((uintptr_t)dx_planes) & 7) == 0) &&
+                 (plane_stride % 4 == 0),
+             "yv_layernorm_bwd: pointers must be 16-byte aligned");
+    const int threads = ((C / 4 + 31) / 32) * 32;
+    const int grid = grid_for(M, LNB_ROWS, 148 * 4);
+    layernorm_bwd_kernel<<<grid, threads, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
+                                                          reinterpret_cast<__nv_bfloat16*>(dx_planes), plane_stride, pre_drop_p,
+                                                          pre_drop_site, reinterpret_cast<const unsigned long long*>(rng), dgamma,
+                                                          dbeta, dbias, M, C);
     YV_LAUNCHED();
 }
 
@@ -645,18 +725,21 @@ extern "C" int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_st
                                 int32_t accumulate, yv_stream_t stream) {
     YV_CHECK(planes && out && rows > 0 && cols > 0, "yv_colsum_planes: bad arguments");
     if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
-    dim3 grid((cols + 127) / 128, (unsigned)((rows + CS_ROWS - 1) / CS_ROWS));
+    dim3 grid((cols + 1023) / 1024, (unsigned)((rows + CSP_ROWS - 1) / CSP_ROWS));
     colsum_planes_kernel<<<grid, 128, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(planes), ld, plane_stride, rows,
                                                       cols, out);
     YV_LAUNCHED();
 }
 
 extern "C" int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux, int64_t ld_aux, int32_t act, void* planes,
-                                int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, yv_stream_t stream) {
+                                int64_t ld_dst, int64_t plane_stride, int64_t rows, int64_t cols, float* dbias,
+                                yv_stream_t stream) {
     YV_CHECK(dy && planes && rows > 0 && cols > 0, "yv_act_bwd_split: bad arguments");
     YV_CHECK(act == YV_ACT_NONE || aux, "yv_act_bwd_split: act %d needs aux", act);
-    act_bwd_split_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, S(stream)>>>(
-        dy, ld_dy, aux, ld_aux, act, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst, plane_stride, rows, cols);
+    if (dbias) YV_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * cols, S(stream)));
+    dim3 grid((unsigned)((cols + 1023) / 1024), (unsigned)((rows + ABS_ROWS - 1) / ABS_ROWS));
+    act_bwd_split_kernel<<<grid, 256, 0, S(stream)>>>(dy, ld_dy, aux, ld_aux, act, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst,
+                                                      plane_stride, rows, cols, dbias);
     YV_LAUNCHED();
 }
 

@@ -185,15 +185,15 @@ def layernorm_fwd(x, gamma, beta, eps, y32, y_planes: Optional[Planes], stats, M
 
 
 def layernorm_bwd(dy, x, gamma, stats, dx32, dx_planes: Optional[Planes], dgamma, dbeta, M, Cdim, *, post_drop_p=0.0,
-                  post_drop_site=0, dx_add=None, pre_drop_p=0.0, pre_drop_site=0, rng=None):
+                  post_drop_site=0, dx_add=None, pre_drop_p=0.0, pre_drop_site=0, rng=None, dbias=None):
     _check(load().yv_layernorm_bwd(C.c_void_p(dy.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()),
                                    C.c_void_p(stats.data_ptr()), C.c_float(post_drop_p), C.c_uint32(post_drop_site),
                                    C.c_void_p(_p(dx_add)), C.c_void_p(_p(dx32)),
                                    C.c_void_p(dx_planes.ptr() if dx_planes is not None else None),
                                    C.c_int64(dx_planes.plane_stride if dx_planes is not None else 0),
                                    C.c_float(pre_drop_p), C.c_uint32(pre_drop_site), C.c_void_p(_p(rng)),
-                                   C.c_void_p(_p(dgamma)), C.c_void_p(_p(dbeta)), C.c_int64(M), C.c_int32(Cdim),
-                                   _stream()), "layernorm_bwd")
+                                   C.c_void_p(_p(dgamma)), C.c_void_p(_p(dbeta)), C.c_void_p(_p(dbias)), C.c_int64(M),
+                                   C.c_int32(Cdim), _stream()), "layernorm_bwd")
 
 
 def softmax_fwd(s, ld_s, mask, rows, cols, rows_per_pair, scale, p_planes: Planes, drop_p=0.0, drop_site=0, rng=None):
@@ -243,13 +243,13 @@ def colsum_planes(p: Planes, out, accumulate=False):
                                    _stream()), "colsum_planes")
 
 
-def act_bwd_split(dy: torch.Tensor, aux: Optional[torch.Tensor], act: int, dst: Planes):
-    """planes = dy * act'(aux); dy / aux are 2-D f32 with unit column stride."""
+def act_bwd_split(dy: torch.Tensor, aux: Optional[torch.Tensor], act: int, dst: Planes, dbias=None):
+    """planes = dy * act'(aux); dy / aux are 2-D f32 with unit column stride; dbias (optional) = column sums."""
     rows, cols = dy.shape
     _check(load().yv_act_bwd_split(C.c_void_p(dy.data_ptr()), C.c_int64(dy.stride(0)), C.c_void_p(_p(aux)),
                                    C.c_int64(aux.stride(0) if aux is not None else 0), C.c_int32(act), C.c_void_p(dst.ptr()),
                                    C.c_int64(dst.ld), C.c_int64(dst.plane_stride), C.c_int64(rows), C.c_int64(cols),
-                                   _stream()), "act_bwd_split")
+                                   C.c_void_p(_p(dbias)), _stream()), "act_bwd_split")
 
 
 def ce_loss(logits, ld, target, rows, cols, loss_sum, count):

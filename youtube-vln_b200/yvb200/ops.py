@@ -230,14 +230,18 @@ def _f32(*shape, device):
 
 
 def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int, N: int, K: int, device,
-                need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None):
-    """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K]."""
-    dx = dW = db = None
+                need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None,
+                db: Optional[torch.Tensor] = None):
+    """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K].
+    ``db`` may arrive precomputed (fused into the kernel that produced ``dp``)."""
+    dx = dW = None
+    have_db = db is not None
     if need_dx:
         dx = _f32(M, K, device=device)
     if need_dw:
         dW = _f32(N, K, device=device)
-        db = _f32(N, device=device)
+        if not have_db:
+            db = _f32(N, device=device)
     fork = r.concurrent and need_dx and need_dw
     if fork:                                    # wgrad + bias grad on the helper stream, dgrad on this one
         cur = torch.cuda.current_stream(device)
@@ -245,7 +249,8 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
-            L.colsum_planes(dp, db)
+            if not have_db:
+                L.colsum_planes(dp, db)
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
         cur.wait_stream(side)
         return dx, dW, db
@@ -253,7 +258,8 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
     if need_dw:
         L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
-        L.colsum_planes(dp, db)
+        if not have_db:
+            L.colsum_planes(dp, db)
     return dx, dW, db
 
 
@@ -289,9 +295,10 @@ class DenseActFn(Function):
         M, N, K = ctx.dims
         dy2 = _c2d(dy)
         dp = Planes.empty(M, N, dy.device)
-        L.act_bwd_split(dy2, ctx.aux, ctx.act, dp)
+        db = _f32(N, device=dy.device) if ctx.needs_input_grad[1] else None
+        L.act_bwd_split(dy2, ctx.aux, ctx.act, dp, db)
         dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dy.device, ctx.needs_input_grad[0],
-                                 ctx.needs_input_grad[1])
+                                 ctx.needs_input_grad[1], db=db)
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None
 
 
@@ -338,12 +345,12 @@ class DenseResLNFn(Function):
         dev = dz.device
         ds = _f32(M, N, device=dev)
         dsp = Planes.empty(M, N, dev)
-        dgamma = torch.zeros(N, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(N, dtype=torch.float32, device=dev)
-        L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, dgamma, dbeta, M, N, pre_drop_p=spec.drop_p,
-                        pre_drop_site=spec.site, rng=r.rng)
-        dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2])
-        return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, dgamma, dbeta, None
+        acc = torch.zeros(3, N, dtype=torch.float32, device=dev)          # dgamma, dbeta, dbias in one memset
+        L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, N, pre_drop_p=spec.drop_p,
+                        pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+        dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2],
+                                 db=acc[2])
+        return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, acc[0], acc[1], None
 
 
 def dense_res_ln(x, res, W, b, gamma, beta, drop_p: float, site: int):
@@ -390,8 +397,10 @@ class DenseActLNFn(Function):
         L.layernorm_bwd(_c2d(dz), g, gamma, stats, dg, None, dgamma, dbeta, M, N)
         dp = Planes.empty(M, N, dev)
         aux = pre if ctx.act == L.ACT_GELU else g
-        L.act_bwd_split(dg, aux, ctx.act, dp)
-        dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        db = _f32(N, device=dev)
+        L.act_bwd_split(dg, aux, ctx.act, dp, db)
+        dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                 db=db)
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, dgamma, dbeta, None
 
 
@@ -713,11 +722,11 @@ class ImageEmbedFn(Function):
         dev = dy.device
         de = _f32(M, H, device=dev)
         dep = Planes.empty(M, H, dev)
-        dgamma = torch.zeros(H, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(H, dtype=torch.float32, device=dev)
+        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)
+        dgamma, dbeta = acc[0], acc[1]
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, dep, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
-                        post_drop_site=spec.site, rng=r.rng)
-        dfeat, dWi, dbi = _linear_bwd(r, dep, ctx.fp, ctx.wp, M, H, F, dev, ctx.needs_input_grad[0], True)
+                        post_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+        dfeat, dWi, dbi = _linear_bwd(r, dep, ctx.fp, ctx.wp, M, H, F, dev, ctx.needs_input_grad[0], True, db=acc[2])
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
         dw5, db5, dw4, db4, dw2, db2, dseq = z(H, 5), z(H), z(H, 4), z(H), z(H, 2), z(H), z(32, H)
         L.embed_loc_bwd(loc2, de, dw5, db5, dw4, db4, dw2, db2, dseq, M, H)
