@@ -93,3 +93,26 @@ YV_DEVINL float yv_warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel lets its successor start launching at once and waits for
+// its predecessors (completion + memory visibility) before touching global memory
+// ---------------------------------------------------------------------------------------------
+YV_DEVINL void yv_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+YV_DEVINL void yv_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool yv_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t yv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = yv_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}

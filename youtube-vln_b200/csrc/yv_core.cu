@@ -2,6 +2,7 @@
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/yvb200.h"
 #include "yv_common.cuh"
@@ -16,6 +17,10 @@ void yv_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool yv_pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("YVB200_PDL"); return e && e[0] == '1'; }();   // opt-in: measured no gain inside the captured step
+    return on;
 }
 void yv_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

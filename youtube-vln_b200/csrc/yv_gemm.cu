@@ -192,6 +192,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int kb_lo = split * p.kb_per_split;
     const int num_kb = min(p.kb_per_split, total_kb - kb_lo);   // >= 1 by construction on the host
     if (threadIdx.x == 0) YV_T(0);
+    yv_pdl_trigger();      // the next kernel may start its own prologue while this one runs
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -213,6 +214,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    yv_pdl_wait();         // barriers, TMEM and descriptors are ready: now wait for the producers of our operands
     if (threadIdx.x == 0) YV_T(1);
 
     if (warp == 0) {
@@ -539,9 +541,9 @@ extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
         attr_set = true;
     }
     if (g->passes == 3)
-        yv_gemm_kernel<3><<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, st>>>(ma, mb, p);
+        YV_CUDA(yv_launch(yv_gemm_kernel<3>, grid, dim3(NUM_THREADS), Cfg<3>::SMEM_BYTES, st, ma, mb, p));
     else
-        yv_gemm_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(ma, mb, p);
+        YV_CUDA(yv_launch(yv_gemm_kernel<1>, grid, dim3(NUM_THREADS), Cfg<1>::SMEM_BYTES, st, ma, mb, p));
     YV_CUDA(cudaGetLastError());
     yv_count_launch();
     return 0;

@@ -18,6 +18,23 @@ constexpr int THREADS = WARPS * 32;
 // ------------------------------------------------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
                                     long long ld_dst, long long plane_stride, long long rows, long long cols) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const bool vec = ((cols & 3) == 0) && ((ld_src & 3) == 0) && ((ld_dst & 3) == 0) && ((plane_stride & 3) == 0) &&
+                     ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)dst) & 7) == 0);
+    if (vec) {
+        const long long c4 = cols >> 2, total = rows * c4;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / c4, c = (i - r * c4) << 2;
+            const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+            __align__(8) __nv_bfloat16 h[4], l[4];
+            yv_split(v.x, h[0], l[0]); yv_split(v.y, h[1], l[1]); yv_split(v.z, h[2], l[2]); yv_split(v.w, h[3], l[3]);
+            *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(dst + plane_stride + r * ld_dst + c) = *reinterpret_cast<uint2*>(l);
+        }
+        return;
+    }
     const long long total = rows * cols;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -32,6 +49,8 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_
 constexpr int SPLIT_BLK = 2048;  // elements per block in the multi-tensor kernel
 __global__ void split_multi_kernel(const YvSplitSeg* __restrict__ segs, int nseg, __nv_bfloat16* __restrict__ planes,
                                    long long plane_stride) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const long long blk = blockIdx.x;
     int lo = 0, hi = nseg - 1;                       // last segment with first_blk <= blk
     while (lo < hi) {
@@ -63,44 +82,93 @@ __global__ void split_multi_kernel(const YvSplitSeg* __restrict__ segs, int nseg
     }
 }
 
-__global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1ULL; }
+__global__ void rng_advance_kernel(unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait(); rng[1] += 1ULL; }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS)
+constexpr int LNF_ROWS = 4;
+__global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yp, long long plane_stride,
                      float* __restrict__ stats, long long M, int C, float drop_p, unsigned drop_site,
                      const unsigned long long* rng) {
-    const int lane = threadIdx.x & 31;
-    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const float* xr = x + row * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += xr[c];
-    const float mean = yv_warp_sum(s) / C;
-    float v = 0.f;
-    for (int c = lane; c < C; c += 32) {
-        const float d = xr[c] - mean;
-        v += d * d;
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    // thread t owns columns [4t, 4t+4); LNF_ROWS rows per block; two block reductions (mean, then centred variance)
+    __shared__ float red[8][LNF_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int c0 = tid * 4;
+    const bool active = c0 < C;
+    const long long row0 = blockIdx.x * (long long)LNF_ROWS;
+    float v[LNF_ROWS][4], part[LNF_ROWS];
+#pragma unroll
+    for (int r = 0; r < LNF_ROWS; ++r) {
+        const long long row = row0 + r;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && row < M) t = *reinterpret_cast<const float4*>(x + row * C + c0);
+        v[r][0] = t.x; v[r][1] = t.y; v[r][2] = t.z; v[r][3] = t.w;
+        part[r] = (t.x + t.y) + (t.z + t.w);
     }
-    const float var = yv_warp_sum(v) / C;
-    const float rstd = 1.f / sqrtf(var + eps);
-    if (stats && lane == 0) {
-        stats[2 * row] = mean;
-        stats[2 * row + 1] = rstd;
+    float mean[LNF_ROWS], rstd[LNF_ROWS];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int r = 0; r < LNF_ROWS; ++r) part[r] = yv_warp_sum(part[r]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < LNF_ROWS; ++r) red[warp][r] = part[r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < LNF_ROWS; ++r) {
+            float t = 0.f;
+            for (int w = 0; w < nwarps; ++w) t += red[w][r];
+            if (pass == 0) {
+                mean[r] = t / C;
+                float q = 0.f;
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d = v[r][j] - mean[r];
+                        q += d * d;
+                    }
+                }
+                part[r] = q;
+            } else {
+                rstd[r] = 1.f / sqrtf(t / C + eps);
+            }
+        }
+        __syncthreads();
     }
+    if (!active) return;
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + c0);
+    const float4 b4 = *reinterpret_cast<const float4*>(beta + c0);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
     const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
-    for (int c = lane; c < C; c += 32) {
-        float y = gamma[c] * ((xr[c] - mean) * rstd) + beta[c];
-        if (drop.thresh) y *= yv_drop_mul(drop, (uint32_t)(row * C + c));
-        if (y32) y32[row * C + c] = y;
+#pragma unroll
+    for (int r = 0; r < LNF_ROWS; ++r) {
+        const long long row = row0 + r;
+        if (row >= M) break;
+        if (stats && tid == 0) {
+            stats[2 * row] = mean[r];
+            stats[2 * row + 1] = rstd[r];
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[j] = gv[j] * ((v[r][j] - mean[r]) * rstd[r]) + bv[j];
+            if (drop.thresh) o[j] *= yv_drop_mul(drop, (uint32_t)(row * C + c0 + j));
+        }
+        if (y32) *reinterpret_cast<float4*>(y32 + row * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
         if (yp) {
-            __nv_bfloat16 h, l;
-            yv_split(y, h, l);
-            yp[row * C + c] = h;
-            yp[plane_stride + row * C + c] = l;
+            __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv_split(o[j], h4[j], l4[j]);
+            *reinterpret_cast<uint2*>(yp + row * C + c0) = *reinterpret_cast<uint2*>(h4);
+            *reinterpret_cast<uint2*>(yp + plane_stride + row * C + c0) = *reinterpret_cast<uint2*>(l4);
         }
     }
 }
@@ -115,6 +183,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxp, long long plane_stride, float pre_p,
                      unsigned pre_site, const unsigned long long* rng, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias, long long M, int C) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float red[8][2 * LNB_ROWS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int c0 = tid * 4;
@@ -204,33 +274,43 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 // ------------------------------------------------------------------------------------------------
 // attention softmax
 // ------------------------------------------------------------------------------------------------
+// one warp per row, the row lives in registers (cols <= 32 * MAXPL): one read and one write of the scores
+template <int MAXPL>
 __global__ void __launch_bounds__(THREADS)
 softmax_fwd_kernel(float* __restrict__ s, long long ld_s, const float* __restrict__ mask, long long rows, int cols,
                    long long rows_per_pair, float scale, __nv_bfloat16* __restrict__ pp, long long ld_p,
                    long long plane_stride, float drop_p, unsigned drop_site, const unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     float* sr = s + row * ld_s;
     const float* mr = mask ? mask + (row / rows_per_pair) * cols : nullptr;
+    float v[MAXPL];
     float mx = -INFINITY;
-    for (int c = lane; c < cols; c += 32) {
-        const float v = sr[c] * scale + (mr ? mr[c] : 0.f);
-        sr[c] = v;
-        mx = fmaxf(mx, v);
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = -INFINITY;
+        if (c < cols) v[i] = sr[c] * scale + (mr ? mr[c] : 0.f);
+        mx = fmaxf(mx, v[i]);
     }
     mx = yv_warp_max(mx);
     float sum = 0.f;
-    for (int c = lane; c < cols; c += 32) {
-        const float e = expf(sr[c] - mx);
-        sr[c] = e;
-        sum += e;
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+        v[i] = (lane + 32 * i < cols) ? expf(v[i] - mx) : 0.f;
+        sum += v[i];
     }
     sum = yv_warp_sum(sum);
     const float inv = 1.f / sum;
     const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
-    for (int c = lane; c < cols; c += 32) {
-        const float pr = sr[c] * inv;
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+        const int c = lane + 32 * i;
+        if (c >= cols) break;
+        const float pr = v[i] * inv;
         sr[c] = pr;
         float pd = pr;
         if (drop.thresh) pd *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
@@ -241,27 +321,38 @@ softmax_fwd_kernel(float* __restrict__ s, long long ld_s, const float* __restric
     }
 }
 
+template <int MAXPL>
 __global__ void __launch_bounds__(THREADS)
 softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd, long long ld_s, long long rows, int cols,
                    float scale, __nv_bfloat16* __restrict__ dsp, long long ld_p, long long plane_stride, float drop_p,
                    unsigned drop_site, const unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const float* pr = p + row * ld_s;
     const float* dr = dpd + row * ld_s;
     const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+    float pv[MAXPL], dv[MAXPL];
     float dot = 0.f;
-    for (int c = lane; c < cols; c += 32) {
-        float d = dr[c];
-        if (drop.thresh) d *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
-        dot += d * pr[c];
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+        const int c = lane + 32 * i;
+        pv[i] = dv[i] = 0.f;
+        if (c < cols) {
+            pv[i] = pr[c];
+            dv[i] = dr[c];
+            if (drop.thresh) dv[i] *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
+            dot += dv[i] * pv[i];
+        }
     }
     dot = yv_warp_sum(dot);
-    for (int c = lane; c < cols; c += 32) {
-        float d = dr[c];
-        if (drop.thresh) d *= yv_drop_mul(drop, (uint32_t)(row * cols + c));
-        const float ds = scale * pr[c] * (d - dot);
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+        const int c = lane + 32 * i;
+        if (c >= cols) break;
+        const float ds = scale * pv[i] * (dv[i] - dot);
         __nv_bfloat16 h, l;
         yv_split(ds, h, l);
         dsp[row * ld_p + c] = h;
@@ -275,6 +366,8 @@ softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd, l
 __global__ void embed_text_fwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ seg,
                                       const float* __restrict__ word, const float* __restrict__ pos,
                                       const float* __restrict__ type, float* __restrict__ out, long long M, int T, int H) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const long long m = blockIdx.x;
     const float* w = word + tok[m] * (long long)H;
     const float* ps = pos + (m % T) * (long long)H;
@@ -285,6 +378,8 @@ __global__ void embed_text_fwd_kernel(const long long* __restrict__ tok, const l
 __global__ void embed_text_bwd_kernel(const long long* __restrict__ tok, const long long* __restrict__ seg,
                                       const float* __restrict__ dout, float* __restrict__ dword, float* __restrict__ dpos,
                                       float* __restrict__ dtype_, long long M, int T, int H, int padding_idx) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const long long m = blockIdx.x;
     const long long t = tok[m];
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
@@ -299,6 +394,8 @@ __global__ void embed_loc_fwd_kernel(const float* __restrict__ loc, const float*
                                      const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ w2,
                                      const float* __restrict__ b2, const float* __restrict__ seq, float* __restrict__ out,
                                      long long M, int H) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const long long m = blockIdx.x;
     __shared__ float l[12];
     if (threadIdx.x < 12) l[threadIdx.x] = loc[m * 12 + threadIdx.x];
@@ -322,6 +419,8 @@ __global__ void embed_loc_bwd_kernel(const float* __restrict__ loc, const float*
                                      float* __restrict__ db5, float* __restrict__ dw4, float* __restrict__ db4,
                                      float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dseq, long long M,
                                      int H) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float l[LOC_ROWS][12];
     const long long r0 = blockIdx.x * (long long)LOC_ROWS;
     const int nr = (int)min((long long)LOC_ROWS, M - r0);
@@ -356,6 +455,8 @@ __global__ void embed_loc_bwd_kernel(const float* __restrict__ loc, const float*
 // ------------------------------------------------------------------------------------------------
 constexpr int CS_ROWS = 64;
 __global__ void colsum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, float* __restrict__ out) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const long long r0 = blockIdx.y * (long long)CS_ROWS;
@@ -367,10 +468,12 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long ld, long lo
 
 // planes variant: x = hi + lo.  Thread owns 8 columns (one 16-byte load per plane per row), a block covers
 // 1024 columns x CSP_ROWS rows; partial sums leave through vector reductions.
-constexpr int CSP_ROWS = 32;
+constexpr int CSP_ROWS = 16;
 __global__ void __launch_bounds__(128)
 colsum_planes_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long plane_stride, long long rows, int cols,
                      float* __restrict__ out) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
     if (c0 >= cols) return;
     const long long r0 = blockIdx.y * (long long)CSP_ROWS;
@@ -404,11 +507,13 @@ colsum_planes_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long lon
 
 // dpre = dy * act'(aux) -> planes   (GELU: aux = pre-activation; ReLU: aux = forward output); optional column sums
 // of dpre (the bias gradient).  Thread owns 4 columns, a block covers 1024 columns x ABS_ROWS rows.
-constexpr int ABS_ROWS = 16;
+constexpr int ABS_ROWS = 4;
 __global__ void __launch_bounds__(256)
 act_bwd_split_kernel(const float* __restrict__ dy, long long ld_dy, const float* __restrict__ aux, long long ld_aux, int act,
                      __nv_bfloat16* __restrict__ dst, long long ld_dst, long long plane_stride, long long rows, long long cols,
                      float* __restrict__ dbias) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     const long long c0 = (blockIdx.x * 256LL + threadIdx.x) * 4;
     if (c0 >= cols) return;
     const long long r0 = blockIdx.y * (long long)ABS_ROWS;
@@ -478,6 +583,8 @@ __device__ float block_sum(float v, float* sh) {
 __global__ void __launch_bounds__(THREADS)
 ce_loss_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ target, int cols,
                float* __restrict__ loss_sum, float* __restrict__ count) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float sh[WARPS];
     const long long row = blockIdx.x;
     const long long t = target[row];
@@ -499,6 +606,8 @@ __global__ void __launch_bounds__(THREADS)
 ce_grad_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ target, int cols,
                const float* __restrict__ count, const float* __restrict__ gscale, float* __restrict__ dl32,
                __nv_bfloat16* __restrict__ dlp, long long ld_p, long long plane_stride) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float sh[WARPS];
     const long long row = blockIdx.x;
     const long long t = target[row];
@@ -530,6 +639,8 @@ ce_grad_kernel(const float* __restrict__ logits, long long ld, const long long* 
 __global__ void __launch_bounds__(THREADS)
 kl_loss_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, long long ld_t,
                const long long* __restrict__ mask, int cols, float* __restrict__ loss_sum, float* __restrict__ count) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float sh[WARPS];
     const long long row = blockIdx.x;
     if (mask[row] == 0) return;
@@ -559,6 +670,8 @@ kl_grad_kernel(const float* __restrict__ logits, long long ld, const float* __re
                const long long* __restrict__ mask, int cols, const float* __restrict__ count,
                const float* __restrict__ gscale, float* __restrict__ dl32, __nv_bfloat16* __restrict__ dlp, long long ld_p,
                long long plane_stride) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
     __shared__ float sh[WARPS];
     const long long row = blockIdx.x;
     const float mk = (float)mask[row];
@@ -610,8 +723,8 @@ inline int grid_for(long long n, int per_block, int cap = 148 * 16) {
 extern "C" int yv_split_planes(const float* src, int64_t ld_src, void* planes, int64_t ld_dst, int64_t plane_stride,
                                int64_t rows, int64_t cols, yv_stream_t stream) {
     YV_CHECK(src && planes && rows > 0 && cols > 0, "yv_split_planes: bad arguments");
-    split_planes_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, S(stream)>>>(
-        src, ld_src, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst, plane_stride, rows, cols);
+    YV_CUDA(yv_launch(split_planes_kernel, dim3(grid_for(rows * cols, 256 * 4)), dim3(256), 0, S(stream), 
+        src, ld_src, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst, plane_stride, rows, cols));
     YV_LAUNCHED();
 }
 
@@ -619,14 +732,14 @@ extern "C" int yv_split_multi(const YvSplitSeg* segs_dev, int32_t nseg, int64_t 
                               int64_t plane_stride, yv_stream_t stream) {
     YV_CHECK(segs_dev && planes && nseg > 0 && total_blocks > 0, "yv_split_multi: bad arguments");
     YV_CHECK(total_blocks < 2147483647LL, "yv_split_multi: too many blocks");
-    split_multi_kernel<<<(unsigned)total_blocks, 256, 0, S(stream)>>>(segs_dev, nseg,
-                                                                      reinterpret_cast<__nv_bfloat16*>(planes), plane_stride);
+    YV_CUDA(yv_launch(split_multi_kernel, dim3((unsigned)total_blocks), dim3(256), 0, S(stream), segs_dev, nseg,
+                                                                      reinterpret_cast<__nv_bfloat16*>(planes), plane_stride));
     YV_LAUNCHED();
 }
 
 extern "C" int yv_rng_advance(uint64_t* rng, yv_stream_t stream) {
     YV_CHECK(rng, "yv_rng_advance: NULL state");
-    rng_advance_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<unsigned long long*>(rng));
+    YV_CUDA(yv_launch(rng_advance_kernel, dim3(1), dim3(1), 0, S(stream), reinterpret_cast<unsigned long long*>(rng)));
     YV_LAUNCHED();
 }
 
@@ -634,9 +747,14 @@ extern "C" int yv_layernorm_fwd(const float* x, const float* gamma, const float*
                                 int64_t plane_stride, float* stats, int64_t M, int32_t C, float drop_p, uint32_t drop_site,
                                 const uint64_t* rng, yv_stream_t stream) {
     YV_CHECK(x && gamma && beta && M > 0 && C > 0 && (y32 || y_planes), "yv_layernorm_fwd: bad arguments");
-    layernorm_fwd_kernel<<<(unsigned)((M + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
-        x, gamma, beta, eps, y32, reinterpret_cast<__nv_bfloat16*>(y_planes), plane_stride, stats, M, C, drop_p, drop_site,
-        reinterpret_cast<const unsigned long long*>(rng));
+    YV_CHECK(C <= 1024 && C % 4 == 0, "yv_layernorm_fwd: hidden size %d must be a multiple of 4 and <= 1024", C);
+    YV_CHECK(((((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)y32) & 15) == 0) &&
+                 ((((uintptr_t)y_planes) & 7) == 0) && (plane_stride % 4 == 0),
+             "yv_layernorm_fwd: pointers must be 16-byte aligned");
+    const int threads = ((C / 4 + 31) / 32) * 32;
+    YV_CUDA(yv_launch(layernorm_fwd_kernel, dim3((unsigned)((M + LNF_ROWS - 1) / LNF_ROWS)), dim3(threads), 0, S(stream), x, gamma,
+                      beta, eps, y32, reinterpret_cast<__nv_bfloat16*>(y_planes), plane_stride, stats, M, C, drop_p, drop_site,
+                      reinterpret_cast<const unsigned long long*>(rng)));
     YV_LAUNCHED();
 }
 
@@ -652,10 +770,10 @@ extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* ga
              "yv_layernorm_bwd: pointers must be 16-byte aligned");
     const int threads = ((C / 4 + 31) / 32) * 32;
     const int grid = grid_for(M, LNB_ROWS, 148 * 4);
-    layernorm_bwd_kernel<<<grid, threads, 0, S(stream)>>>(dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
+    YV_CUDA(yv_launch(layernorm_bwd_kernel, dim3(grid), dim3(threads), 0, S(stream), dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,
                                                           reinterpret_cast<__nv_bfloat16*>(dx_planes), plane_stride, pre_drop_p,
                                                           pre_drop_site, reinterpret_cast<const unsigned long long*>(rng), dgamma,
-                                                          dbeta, dbias, M, C);
+                                                          dbeta, dbias, M, C));
     YV_LAUNCHED();
 }
 
@@ -663,9 +781,18 @@ extern "C" int yv_softmax_fwd(float* s, int64_t ld_s, const float* mask, int64_t
                               float scale, void* p_planes, int64_t ld_p, int64_t plane_stride, float drop_p,
                               uint32_t drop_site, const uint64_t* rng, yv_stream_t stream) {
     YV_CHECK(s && p_planes && rows > 0 && cols > 0 && rows_per_pair > 0, "yv_softmax_fwd: bad arguments");
-    softmax_fwd_kernel<<<(unsigned)((rows + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
-        s, ld_s, mask, rows, cols, rows_per_pair, scale, reinterpret_cast<__nv_bfloat16*>(p_planes), ld_p, plane_stride, drop_p,
-        drop_site, reinterpret_cast<const unsigned long long*>(rng));
+    YV_CHECK(cols <= 2048, "yv_softmax_fwd: %d keys per row not supported (max 2048)", cols);
+    const dim3 grid((unsigned)((rows + WARPS - 1) / WARPS));
+    auto* pp = reinterpret_cast<__nv_bfloat16*>(p_planes);
+    auto* rp = reinterpret_cast<const unsigned long long*>(rng);
+#define YV_SMF(PL) YV_CUDA(yv_launch(softmax_fwd_kernel<PL>, grid, dim3(THREADS), 0, S(stream), s, ld_s, mask, rows, cols, \
+                                     rows_per_pair, scale, pp, ld_p, plane_stride, drop_p, drop_site, rp))
+    if (cols <= 96) YV_SMF(3);
+    else if (cols <= 288) YV_SMF(9);
+    else if (cols <= 576) YV_SMF(18);
+    else if (cols <= 1152) YV_SMF(36);
+    else YV_SMF(64);
+#undef YV_SMF
     YV_LAUNCHED();
 }
 
@@ -673,26 +800,35 @@ extern "C" int yv_softmax_bwd(const float* p, const float* dpd, int64_t ld_s, in
                               void* ds_planes, int64_t ld_p, int64_t plane_stride, float drop_p, uint32_t drop_site,
                               const uint64_t* rng, yv_stream_t stream) {
     YV_CHECK(p && dpd && ds_planes && rows > 0 && cols > 0, "yv_softmax_bwd: bad arguments");
-    softmax_bwd_kernel<<<(unsigned)((rows + WARPS - 1) / WARPS), THREADS, 0, S(stream)>>>(
-        p, dpd, ld_s, rows, cols, scale, reinterpret_cast<__nv_bfloat16*>(ds_planes), ld_p, plane_stride, drop_p, drop_site,
-        reinterpret_cast<const unsigned long long*>(rng));
+    YV_CHECK(cols <= 2048, "yv_softmax_bwd: %d keys per row not supported (max 2048)", cols);
+    const dim3 grid((unsigned)((rows + WARPS - 1) / WARPS));
+    auto* dp = reinterpret_cast<__nv_bfloat16*>(ds_planes);
+    auto* rp = reinterpret_cast<const unsigned long long*>(rng);
+#define YV_SMB(PL) YV_CUDA(yv_launch(softmax_bwd_kernel<PL>, grid, dim3(THREADS), 0, S(stream), p, dpd, ld_s, rows, cols, scale, \
+                                     dp, ld_p, plane_stride, drop_p, drop_site, rp))
+    if (cols <= 96) YV_SMB(3);
+    else if (cols <= 288) YV_SMB(9);
+    else if (cols <= 576) YV_SMB(18);
+    else if (cols <= 1152) YV_SMB(36);
+    else YV_SMB(64);
+#undef YV_SMB
     YV_LAUNCHED();
 }
 
 extern "C" int yv_embed_text_fwd(const int64_t* tok, const int64_t* seg, const float* word, const float* pos,
                                  const float* type, float* out, int64_t M, int32_t T, int32_t H, yv_stream_t stream) {
     YV_CHECK(tok && seg && word && pos && type && out && M > 0, "yv_embed_text_fwd: bad arguments");
-    embed_text_fwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(tok),
-                                                              reinterpret_cast<const long long*>(seg), word, pos, type, out, M, T, H);
+    YV_CUDA(yv_launch(embed_text_fwd_kernel, dim3((unsigned)M), dim3(256), 0, S(stream), reinterpret_cast<const long long*>(tok),
+                                                              reinterpret_cast<const long long*>(seg), word, pos, type, out, M, T, H));
     YV_LAUNCHED();
 }
 
 extern "C" int yv_embed_text_bwd(const int64_t* tok, const int64_t* seg, const float* dout, float* dword, float* dpos,
                                  float* dtype_, int64_t M, int32_t T, int32_t H, int32_t padding_idx, yv_stream_t stream) {
     YV_CHECK(tok && seg && dout && M > 0, "yv_embed_text_bwd: bad arguments");
-    embed_text_bwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(tok),
+    YV_CUDA(yv_launch(embed_text_bwd_kernel, dim3((unsigned)M), dim3(256), 0, S(stream), reinterpret_cast<const long long*>(tok),
                                                               reinterpret_cast<const long long*>(seg), dout, dword, dpos, dtype_, M,
-                                                              T, H, padding_idx);
+                                                              T, H, padding_idx));
     YV_LAUNCHED();
 }
 
@@ -700,15 +836,15 @@ extern "C" int yv_embed_loc_fwd(const float* loc, const float* w5, const float* 
                                 const float* w2, const float* b2, const float* seq, float* out, int64_t M, int32_t H,
                                 yv_stream_t stream) {
     YV_CHECK(loc && w5 && b5 && w4 && b4 && w2 && b2 && seq && out && M > 0, "yv_embed_loc_fwd: bad arguments");
-    embed_loc_fwd_kernel<<<(unsigned)M, 256, 0, S(stream)>>>(loc, w5, b5, w4, b4, w2, b2, seq, out, M, H);
+    YV_CUDA(yv_launch(embed_loc_fwd_kernel, dim3((unsigned)M), dim3(256), 0, S(stream), loc, w5, b5, w4, b4, w2, b2, seq, out, M, H));
     YV_LAUNCHED();
 }
 
 extern "C" int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5, float* db5, float* dw4, float* db4, float* dw2,
                                 float* db2, float* dseq, int64_t M, int32_t H, yv_stream_t stream) {
     YV_CHECK(loc && dout && dw5 && db5 && dw4 && db4 && dw2 && db2 && dseq && M > 0, "yv_embed_loc_bwd: bad arguments");
-    embed_loc_bwd_kernel<<<(unsigned)((M + LOC_ROWS - 1) / LOC_ROWS), 256, 0, S(stream)>>>(loc, dout, dw5, db5, dw4, db4, dw2,
-                                                                                          db2, dseq, M, H);
+    YV_CUDA(yv_launch(embed_loc_bwd_kernel, dim3((unsigned)((M + LOC_ROWS - 1) / LOC_ROWS)), dim3(256), 0, S(stream), loc, dout, dw5, db5, dw4, db4, dw2,
+                                                                                          db2, dseq, M, H));
     YV_LAUNCHED();
 }
 
@@ -717,7 +853,7 @@ extern "C" int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols,
     YV_CHECK(x && out && rows > 0 && cols > 0, "yv_colsum: bad arguments");
     if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
     dim3 grid((cols + 127) / 128, (unsigned)((rows + CS_ROWS - 1) / CS_ROWS));
-    colsum_kernel<<<grid, 128, 0, S(stream)>>>(x, ld, rows, cols, out);
+    YV_CUDA(yv_launch(colsum_kernel, dim3(grid), dim3(128), 0, S(stream), x, ld, rows, cols, out));
     YV_LAUNCHED();
 }
 
@@ -726,8 +862,8 @@ extern "C" int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_st
     YV_CHECK(planes && out && rows > 0 && cols > 0, "yv_colsum_planes: bad arguments");
     if (!accumulate) YV_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, S(stream)));
     dim3 grid((cols + 1023) / 1024, (unsigned)((rows + CSP_ROWS - 1) / CSP_ROWS));
-    colsum_planes_kernel<<<grid, 128, 0, S(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(planes), ld, plane_stride, rows,
-                                                      cols, out);
+    YV_CUDA(yv_launch(colsum_planes_kernel, dim3(grid), dim3(128), 0, S(stream), reinterpret_cast<const __nv_bfloat16*>(planes), ld, plane_stride, rows,
+                                                      cols, out));
     YV_LAUNCHED();
 }
 
@@ -738,16 +874,16 @@ extern "C" int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux
     YV_CHECK(act == YV_ACT_NONE || aux, "yv_act_bwd_split: act %d needs aux", act);
     if (dbias) YV_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * cols, S(stream)));
     dim3 grid((unsigned)((cols + 1023) / 1024), (unsigned)((rows + ABS_ROWS - 1) / ABS_ROWS));
-    act_bwd_split_kernel<<<grid, 256, 0, S(stream)>>>(dy, ld_dy, aux, ld_aux, act, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst,
-                                                      plane_stride, rows, cols, dbias);
+    YV_CUDA(yv_launch(act_bwd_split_kernel, dim3(grid), dim3(256), 0, S(stream), dy, ld_dy, aux, ld_aux, act, reinterpret_cast<__nv_bfloat16*>(planes), ld_dst,
+                                                      plane_stride, rows, cols, dbias));
     YV_LAUNCHED();
 }
 
 extern "C" int yv_ce_loss(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int32_t cols, float* loss_sum,
                           float* count, yv_stream_t stream) {
     YV_CHECK(logits && target && loss_sum && count && rows > 0 && cols > 0, "yv_ce_loss: bad arguments");
-    ce_loss_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target), cols,
-                                                             loss_sum, count);
+    YV_CUDA(yv_launch(ce_loss_kernel, dim3((unsigned)rows), dim3(THREADS), 0, S(stream), logits, ld, reinterpret_cast<const long long*>(target), cols,
+                                                             loss_sum, count));
     YV_LAUNCHED();
 }
 
@@ -755,17 +891,17 @@ extern "C" int yv_ce_grad(const float* logits, int64_t ld, const int64_t* target
                           const float* gscale, float* dl32, void* dl_planes, int64_t ld_p, int64_t plane_stride,
                           yv_stream_t stream) {
     YV_CHECK(logits && target && count && (dl32 || dl_planes) && rows > 0 && cols > 0, "yv_ce_grad: bad arguments");
-    ce_grad_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target), cols, count,
+    YV_CUDA(yv_launch(ce_grad_kernel, dim3((unsigned)rows), dim3(THREADS), 0, S(stream), logits, ld, reinterpret_cast<const long long*>(target), cols, count,
                                                              gscale, dl32, reinterpret_cast<__nv_bfloat16*>(dl_planes), ld_p,
-                                                             plane_stride);
+                                                             plane_stride));
     YV_LAUNCHED();
 }
 
 extern "C" int yv_kl_loss(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* mask, int64_t rows,
                           int32_t cols, float* loss_sum, float* count, yv_stream_t stream) {
     YV_CHECK(logits && target && mask && loss_sum && count && rows > 0 && cols > 0, "yv_kl_loss: bad arguments");
-    kl_loss_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
-                                                             cols, loss_sum, count);
+    YV_CUDA(yv_launch(kl_loss_kernel, dim3((unsigned)rows), dim3(THREADS), 0, S(stream), logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
+                                                             cols, loss_sum, count));
     YV_LAUNCHED();
 }
 
@@ -773,8 +909,8 @@ extern "C" int yv_kl_grad(const float* logits, int64_t ld, const float* target, 
                           int32_t cols, const float* count, const float* gscale, float* dl32, void* dl_planes, int64_t ld_p,
                           int64_t plane_stride, yv_stream_t stream) {
     YV_CHECK(logits && target && mask && count && (dl32 || dl_planes) && rows > 0 && cols > 0, "yv_kl_grad: bad arguments");
-    kl_grad_kernel<<<(unsigned)rows, THREADS, 0, S(stream)>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
+    YV_CUDA(yv_launch(kl_grad_kernel, dim3((unsigned)rows), dim3(THREADS), 0, S(stream), logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
                                                              cols, count, gscale, dl32, reinterpret_cast<__nv_bfloat16*>(dl_planes),
-                                                             ld_p, plane_stride);
+                                                             ld_p, plane_stride));
     YV_LAUNCHED();
 }
