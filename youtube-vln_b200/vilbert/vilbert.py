@@ -635,7 +635,7 @@ class BertLMPredictionHead(nn.Module):
     def forward(self, hidden_states):
         h = self.transform(hidden_states)
         if h.is_cuda:
-            return _cuda_ops(h).dense_act(h, self.decoder.weight, self.bias, 0, want_planes=False)
+            return _cuda_ops(h).dense_act(h, self.decoder.weight, self.bias, 0, want_planes=False, pad_out=True)
         return self.decoder(h) + self.bias
 
 
@@ -668,7 +668,7 @@ class BertImagePredictionHead(nn.Module):
     def forward(self, hidden_states):
         h = self.transform(hidden_states)
         if h.is_cuda:
-            return _cuda_ops(h).dense_act(h, self.decoder.weight, self.decoder.bias, 0, want_planes=False)
+            return _cuda_ops(h).dense_act(h, self.decoder.weight, self.decoder.bias, 0, want_planes=False, pad_out=True)
         return self.decoder(h)
 
 

@@ -21,10 +21,10 @@ class CELossFn(Function):
     @staticmethod
     def forward(ctx, logits, target):
         R, V = logits.shape
-        assert logits.is_contiguous() and logits.dtype == torch.float32
+        assert logits.stride(1) == 1 and logits.dtype == torch.float32     # rows may be padded (stride(0) >= V)
         target = target.contiguous().long()
         acc = torch.zeros(2, dtype=torch.float32, device=logits.device)     # {loss_sum, count}
-        L.ce_loss(logits, V, target, R, V, acc[0:1], acc[1:2])
+        L.ce_loss(logits, logits.stride(0), target, R, V, acc[0:1], acc[1:2])
         ctx.save_for_backward(logits, target, acc)
         return acc[0] / acc[1].clamp_min(1.0)
 
@@ -32,20 +32,21 @@ class CELossFn(Function):
     def backward(ctx, g):
         logits, target, acc = ctx.saved_tensors
         R, V = logits.shape
-        dl = torch.empty_like(logits)
-        L.ce_grad(logits, V, target, R, V, acc[1:2], g.contiguous().float().reshape(1), dl, None)
-        return dl, None
+        ld = logits.stride(0)
+        dl = torch.empty((R, ld), dtype=torch.float32, device=logits.device)
+        L.ce_grad(logits, ld, target, R, V, acc[1:2], g.contiguous().float().reshape(1), dl, None)
+        return dl[:, :V], None
 
 
 class KLLossFn(Function):
     @staticmethod
     def forward(ctx, logits, target, mask):
         R, Cc = logits.shape
-        assert logits.is_contiguous() and logits.dtype == torch.float32
+        assert logits.stride(1) == 1 and logits.dtype == torch.float32
         target = target.contiguous().float()
         mask = mask.contiguous().long()
         acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
-        L.kl_loss(logits, Cc, target, Cc, mask, R, Cc, acc[0:1], acc[1:2])
+        L.kl_loss(logits, logits.stride(0), target, Cc, mask, R, Cc, acc[0:1], acc[1:2])
         ctx.save_for_backward(logits, target, mask, acc)
         return acc[0] / acc[1].clamp_min(1.0)
 
@@ -53,17 +54,31 @@ class KLLossFn(Function):
     def backward(ctx, g):
         logits, target, mask, acc = ctx.saved_tensors
         R, Cc = logits.shape
-        dl = torch.empty_like(logits)
-        L.kl_grad(logits, Cc, target, Cc, mask, R, Cc, acc[1:2], g.contiguous().float().reshape(1), dl, None)
-        return dl, None, None
+        ld = logits.stride(0)
+        dl = torch.empty((R, ld), dtype=torch.float32, device=logits.device)
+        L.kl_grad(logits, ld, target, Cc, mask, R, Cc, acc[1:2], g.contiguous().float().reshape(1), dl, None)
+        return dl[:, :Cc], None, None
+
+
+def _rows(logits: torch.Tensor) -> torch.Tensor:
+    """[..., V] -> 2-D view; keeps the padded row pitch of the drop-in's logits (no copy)."""
+    if logits.dim() == 2:
+        return logits
+    try:
+        v = logits.view(-1, logits.shape[-1])
+        if v.stride(1) == 1:
+            return v
+    except RuntimeError:
+        pass
+    return logits.reshape(-1, logits.shape[-1]).contiguous()
 
 
 def language_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    return CELossFn.apply(logits.reshape(-1, logits.shape[-1]), target.reshape(-1))
+    return CELossFn.apply(_rows(logits), target.reshape(-1))
 
 
 def vision_loss(logits: torch.Tensor, target: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    return KLLossFn.apply(logits.reshape(-1, logits.shape[-1]), target.reshape(-1, target.shape[-1]), mask.reshape(-1))
+    return KLLossFn.apply(_rows(logits), target.reshape(-1, target.shape[-1]), mask.reshape(-1))
 
 
 def step_losses(batch: List[torch.Tensor], outputs: Dict[str, torch.Tensor], args, training: bool = True,

@@ -208,6 +208,13 @@ def _c2d(x: torch.Tensor) -> torch.Tensor:
         x = x.float()
     if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) >= x.shape[1]:
         return x                       # row-strided 2-D views (e.g. hidden[:, 0]) are consumed in place
+    if x.dim() > 2 and not x.is_contiguous():
+        try:
+            x2 = x.view(-1, x.shape[-1])            # padded-row views (logits with ld > cols) stay in place
+            if x2.stride(1) == 1:
+                return x2
+        except RuntimeError:
+            pass
     x2 = x.reshape(-1, x.shape[-1])
     return x2 if x2.is_contiguous() else x2.contiguous()
 
@@ -277,16 +284,20 @@ class DenseActFn(Function):
         wp = r.arena.get((W,))
         act = spec.act
         need = any(ctx.needs_input_grad)
-        y = _f32(M, N, device=x.device)
+        # rows of wide, oddly sized outputs (30522 / 1601 logits) are padded to 8 floats so every store is a float4
+        ldN = (N + 7) // 8 * 8 if getattr(spec, "pad_out", False) else N
+        y = _f32(M, ldN, device=x.device)
         yp = Planes.empty(M, N, x.device) if spec.want_planes else None
         pre = _f32(M, N, device=x.device) if (act == L.ACT_GELU and need) else None
-        L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, act=act, aux_out=pre, out32=y, ld_out=N,
+        L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, act=act, aux_out=pre, out32=y, ld_out=ldN,
                out_planes=yp.ptr() if yp else None, ld_pl=yp.ld if yp else 0,
                pl_plane_stride=yp.plane_stride if yp else 0)
         ctx.r, ctx.xp, ctx.wp, ctx.act, ctx.dims = r, xp, wp, act, (M, N, K)
         ctx.aux = pre if act == L.ACT_GELU else (y if act == L.ACT_RELU else None)
         ctx.xshape = x.shape
         spec.out_planes = yp
+        if ldN != N:
+            return y[:, :N].view(*x.shape[:-1], N)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -302,8 +313,8 @@ class DenseActFn(Function):
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None
 
 
-def dense_act(x, W, b, act: int, want_planes: bool = True):
-    spec = types.SimpleNamespace(act=act, want_planes=want_planes, out_planes=None)
+def dense_act(x, W, b, act: int, want_planes: bool = True, pad_out: bool = False):
+    spec = types.SimpleNamespace(act=act, want_planes=want_planes, out_planes=None, pad_out=pad_out)
     y = DenseActFn.apply(x, W, b, spec)
     if spec.out_planes is not None:
         attach_planes(y, spec.out_planes)
