@@ -249,6 +249,32 @@ def main():
                 "algorithmic_gflop_per_step": g_flop / 1e9, "tensor_pipe_flop_multiplier": hw_mult,
                 "frac_of_tensor_pipe": achieved * hw_mult / peak_tf}
 
+    # informational: the same step issued as stock PyTorch fp32 ops on this GPU (the oracle restatement on CUDA
+    # tensors, eval-mode dropout, TF32 off) -- what the reference's unfused ATen path costs on a B200
+    torch_gpu = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import vilbert_oracle as O
+        torch.backends.cuda.matmul.allow_tf32 = False
+        sd = {k: v.to(dev).requires_grad_(True) for k, v in synth.lily_state_dict(cfg, seed=0).items()
+              if not k.endswith("cls.predictions.decoder.weight")}
+        dbatch = [t.to(dev) if torch.is_tensor(t) else t for t in synth.make_batch(WORKLOAD, seed=1)]
+        for _ in range(2):
+            O.oracle_step(sd, cfg, args, dbatch, clone=False)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            O.oracle_step(sd, cfg, args, dbatch, clone=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        torch_gpu = {"ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT,
+                     "what": "oracle restatement as eager torch fp32 ops on cuda:0 (no dropout, TF32 off)"}
+        del sd, dbatch
+    except Exception as e:  # informational only
+        torch_gpu = {"error": repr(e)[:200]}
+
     cpu = None
     if not a.no_cpu_baseline:
         v, sec, cores = run_cpu_oracle(2, 1)
@@ -264,6 +290,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / a.steps * 1e3},
             "gpu_launches": step.launches_per_step * a.steps, "gpu_launches_per_step": step.launches_per_step,
             "cuda_graph": not a.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "torch_ops_on_gpu": torch_gpu,
             "train_tflops_algorithmic": value * TRAIN_GFLOP_PER_PAIR / 1e3, "final_loss": final_loss}
     print(json.dumps(line))
     if world > 1:

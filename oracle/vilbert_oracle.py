@@ -112,7 +112,7 @@ def connection_layer(v, v_mask, t, t_mask, sd, p, n_heads):
 
 
 def text_embeddings(tokens, segs, sd, p="bert.embeddings"):
-    pos = torch.arange(tokens.shape[1])
+    pos = torch.arange(tokens.shape[1], device=tokens.device)
     e = sd[p + ".word_embeddings.weight"][tokens] + sd[p + ".position_embeddings.weight"][pos][None] \
         + sd[p + ".token_type_embeddings.weight"][segs]
     return layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"])
@@ -135,7 +135,7 @@ def bert_model(sd, cfg, tokens, feat, loc, segs=None, tmask=None, vmask=None):
     if segs is None:
         segs = torch.zeros_like(tokens)
     if vmask is None:
-        vmask = torch.ones(feat.shape[0], feat.shape[1], dtype=tokens.dtype)
+        vmask = torch.ones(feat.shape[0], feat.shape[1], dtype=tokens.dtype, device=tokens.device)
     t_add = ((1.0 - tmask.to(dt)) * -10000.0)[:, None, None, :]
     v_add = ((1.0 - vmask.to(dt)) * -10000.0)[:, None, None, :]
     t = text_embeddings(tokens, segs, sd)
@@ -194,7 +194,7 @@ def lily_forward(sd, cfg, args, tokens, feat, loc, segs=None, tmask=None, vmask=
 def pad_packed(t, mask):
     """utils/dataset/common.py:21-26."""
     mask = mask.bool()
-    out = torch.full(mask.shape, -float("inf"), dtype=t.dtype)
+    out = torch.full(mask.shape, -float("inf"), dtype=t.dtype, device=t.device)
     out = out.masked_scatter(mask, t)
     return out
 
@@ -228,7 +228,7 @@ def losses(batch: List[torch.Tensor], outputs: Dict[str, torch.Tensor], args, tr
             res["ranking"] = F.binary_cross_entropy_with_logits(pred, target.to(pred.dtype))
     if "traj" in outputs:
         pred = pad_packed(outputs["traj"].squeeze(1), opt_mask)
-        target = torch.zeros(pred.shape, dtype=torch.bool)
+        target = torch.zeros(pred.shape, dtype=torch.bool, device=pred.device)
         if not (args.ranking or args.not_traj_judge_data):
             target[:, 0] = 1
         elif args.pretrain:
@@ -254,10 +254,16 @@ def total_loss(loss_dict, args):
     return tot
 
 
-def oracle_step(sd: Dict[str, torch.Tensor], cfg, args, batch, dtype=torch.float32, want_grads=True):
-    """Forward + all active losses (+ autograd backward).  Returns (outputs, loss_dict, total, grads)."""
-    sd = {k: v.detach().to(dtype).clone().requires_grad_(want_grads) for k, v in sd.items()
-          if not k.endswith("cls.predictions.decoder.weight")}
+def oracle_step(sd: Dict[str, torch.Tensor], cfg, args, batch, dtype=torch.float32, want_grads=True, clone=True):
+    """Forward + all active losses (+ autograd backward).  Returns (outputs, loss_dict, total, grads).
+    Runs on whatever device ``sd`` / ``batch`` live on (the host for parity checks; bench.py also times it on
+    the GPU as the "stock PyTorch ops" comparison)."""
+    if clone:
+        sd = {k: v.detach().to(dtype).clone().requires_grad_(want_grads) for k, v in sd.items()
+              if not k.endswith("cls.predictions.decoder.weight")}
+    else:
+        for v in sd.values():
+            v.grad = None
     m = batch[13]
     co = batch[11]
     tokens, feat, loc, segs, tmask, vmask = batch[6][m], batch[1][m], batch[2][m], batch[10][m], batch[7][m], batch[3][m]
