@@ -15,10 +15,83 @@ from . import fused, lib, ops, synth
 _FLOAT_FIELDS = (1, 2, 4)          # image_features, image_locations, image_targets
 
 
+class GradientExchange:
+    """Data-parallel gradient averaging overlapped with backward.
+
+    A post-accumulate hook on every parameter collects finished gradients into ~``bucket_mb`` buckets; a full
+    bucket is all-reduced (NCCL ``AVG``, one grouped launch for all its tensors) on a communication stream that
+    only waits for the backward work issued so far.  Under ``torch.cuda.graph`` capture the collectives become
+    graph nodes on a parallel branch, so every replay overlaps them with the remaining backward kernels.  The
+    reference gets the same effect from ``DistributedDataParallel`` bucket hooks (utils/distributed.py:97-99).
+    """
+
+    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 64.0):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.bucket_bytes = int(bucket_mb * 2 ** 20)
+        self.pending: List[torch.Tensor] = []
+        self.pending_bytes = 0
+        self.device = next(model.parameters()).device
+        self.comm = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.avg = dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+        self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
+                        if p.requires_grad]
+        self.launched = 0
+
+    def _on_grad(self, p: torch.Tensor):
+        g = p.grad
+        if g is None:
+            return
+        self.pending.append(g)
+        self.pending_bytes += g.numel() * g.element_size()
+        if self.pending_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if not self.pending:
+            return
+        grads, self.pending, self.pending_bytes = self.pending, [], 0
+        if self.comm is not None:
+            cur = torch.cuda.current_stream(self.device)
+            self.comm.wait_stream(cur)
+            with torch.cuda.stream(self.comm):
+                self._reduce(grads)
+        else:
+            self._reduce(grads)
+        self.launched += 1
+
+    def _reduce(self, grads):
+        dist = self.dist
+        if self.avg == dist.ReduceOp.AVG:           # NCCL: one grouped launch, averaging inside the collective
+            with dist._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=self.avg, group=self.group)
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])        # gloo (CPU tests): flatten, sum, scatter back
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(float(self.world))
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    def finish(self):
+        """Reduce the last partial bucket and make the current stream wait for all communication."""
+        self._flush()
+        if self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 class GraphedStep:
     def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
-                 refresh_weights_each_step: bool = True, warmup: int = 2):
+                 refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
         self.model, self.args = model, args
+        self.exchange = exchange
         self.device = next(model.parameters()).device
         self.rt = ops.rt(self.device)
         self.refresh = refresh_weights_each_step
@@ -71,6 +144,8 @@ class GraphedStep:
         if "traj" in ld:
             tot = tot + self.args.traj_loss_scale * ld["traj"]
         tot.backward()
+        if self.exchange is not None:
+            self.exchange.finish()
         self.loss = tot.detach()
 
     def load(self, batch: List[torch.Tensor]):
