@@ -125,8 +125,9 @@ def main():
     config = {"workload": f"{WORKLOAD}: full ViLBERT 12t/6v/6c pretrain step (vision+language+ranking+traj), "
                           f"{wl['frames']} frames x {wl['boxes']} regions, {wl['tokens']} tokens, {pairs} pairs/GPU",
               "pairs_per_gpu": pairs, "parallelism": f"dp{a.gpus}", "precision": a.precision,
-              "gradient_exchange": "none (1 GPU)" if a.gpus == 1 else "64 MB buckets, NCCL AVG all-reduce captured in "
-                                   "the step graph on a communication stream (overlaps backward)",
+              "gradient_exchange": "none (1 GPU)" if a.gpus == 1 else (
+                  "64 MB buckets, grouped NCCL AVG all-reduce " + ("captured in the step graph (overlaps backward)"
+                  if os.environ.get("YVB200_CAPTURE_NCCL", "0") == "1" else "issued after the graph replay")),
               "l2": "flushed between timed steps (256 MB write); per-step working set ~3 GB >> 126 MB L2"}
 
     if a.impl == "reference":
@@ -151,6 +152,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     os.environ["YVB200_PRECISION"] = a.precision
     from yvb200 import lib, ops

@@ -38,10 +38,21 @@ class GradientExchange:
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
                         if p.requires_grad]
         self.launched = 0
+        self.defer = False          # True: hooks do nothing, ``reduce_all`` exchanges every gradient after backward
+
+    def reduce_all(self, model: torch.nn.Module):
+        """Bucketed exchange of all gradients (used when the collectives are not part of a captured graph)."""
+        for p in model.parameters():
+            if p.grad is not None:
+                self.pending.append(p.grad)
+                self.pending_bytes += p.grad.numel() * p.grad.element_size()
+                if self.pending_bytes >= self.bucket_bytes:
+                    self._flush()
+        self.finish()
 
     def _on_grad(self, p: torch.Tensor):
         g = p.grad
-        if g is None:
+        if g is None or self.defer:
             return
         self.pending.append(g)
         self.pending_bytes += g.numel() * g.element_size()
@@ -92,6 +103,13 @@ class GraphedStep:
                  refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
         self.model, self.args = model, args
         self.exchange = exchange
+        # NCCL collectives inside the captured graph overlap the exchange with backward; opt-in because a capture
+        # with live communicator threads needs thread-local capture mode (YVB200_CAPTURE_NCCL=1).  Default: the
+        # bucketed exchange runs right after the replay on the communication stream.
+        import os as _os
+        self.capture_exchange = exchange is not None and _os.environ.get("YVB200_CAPTURE_NCCL", "0") == "1"
+        if exchange is not None and not self.capture_exchange:
+            exchange.defer = True
         self.device = next(model.parameters()).device
         self.rt = ops.rt(self.device)
         self.refresh = refresh_weights_each_step
@@ -114,7 +132,8 @@ class GraphedStep:
             self._zero_grads()
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.launch_count()
-            with torch.cuda.graph(self.graph):
+            mode = "thread_local" if self.capture_exchange else "global"
+            with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self._body()
             self.launches_per_step = lib.launch_count() - n0
         else:
@@ -144,7 +163,7 @@ class GraphedStep:
         if "traj" in ld:
             tot = tot + self.args.traj_loss_scale * ld["traj"]
         tot.backward()
-        if self.exchange is not None:
+        if self.exchange is not None and self.capture_exchange:
             self.exchange.finish()
         self.loss = tot.detach()
 
@@ -164,4 +183,6 @@ class GraphedStep:
         else:
             self._zero_grads()
             self._body()
+        if self.exchange is not None and not self.capture_exchange:
+            self.exchange.reduce_all(self.model)
         return self.loss
