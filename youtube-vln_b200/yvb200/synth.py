@@ -62,6 +62,13 @@ WORKLOADS = {
     "cfg4_p4": dict(config="full", bs=2, cands=4, frames=4, boxes=36, tokens=80),
     "cfg4_p16": dict(config="full", bs=2, cands=4, frames=16, boxes=36, tokens=80),
     "cfg4_p32": dict(config="full", bs=2, cands=4, frames=32, boxes=36, tokens=80),
+    # 2-pair versions of the trajectory-length sweep: small enough for the host oracle inside a test
+    "cfg4_p4_n2": dict(config="full", bs=1, cands=2, frames=4, boxes=36, tokens=80, args=dict(pretrain=False)),
+    "cfg4_p16_n2": dict(config="full", bs=1, cands=2, frames=16, boxes=36, tokens=80, args=dict(pretrain=False)),
+    "cfg4_p32_n2": dict(config="full", bs=1, cands=2, frames=32, boxes=36, tokens=80, args=dict(pretrain=False)),
+    # fine-tune style: ranking objective only (BASELINE config 3 shape, 16 pairs)
+    "cfg3_rank": dict(config="full", bs=4, cands=4, frames=8, boxes=36, tokens=80,
+                      args=dict(pretrain=False, masked_vision=False, masked_language=False, traj_judge=False)),
 }
 
 
