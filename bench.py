@@ -125,9 +125,9 @@ def main():
     config = {"workload": f"{WORKLOAD}: full ViLBERT 12t/6v/6c pretrain step (vision+language+ranking+traj), "
                           f"{wl['frames']} frames x {wl['boxes']} regions, {wl['tokens']} tokens, {pairs} pairs/GPU",
               "pairs_per_gpu": pairs, "parallelism": f"dp{a.gpus}", "precision": a.precision,
-              "gradient_exchange": "none (1 GPU)" if a.gpus == 1 else (
-                  "64 MB buckets, grouped NCCL AVG all-reduce " + ("captured in the step graph (overlaps backward)"
-                  if os.environ.get("YVB200_CAPTURE_NCCL", "0") == "1" else "issued after the graph replay")),
+              "gradient_exchange": "none (1 GPU)" if a.gpus == 1 else
+              "160 MB segments closed by external CUDA events inside the step graph; grouped NCCL AVG all-reduce per "
+              "segment on a communication stream while the rest of backward runs",
               "l2": "flushed between timed steps (256 MB write); per-step working set ~3 GB >> 126 MB L2"}
 
     if a.impl == "reference":
@@ -150,10 +150,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device for --impl ours (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    force_exchange = world == 1 and os.environ.get("YVB200_FORCE_EXCHANGE", "0") == "1"   # debugging aid
+    if world > 1 or force_exchange:
         import torch.distributed as dist
-        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        dist.init_process_group("nccl", device_id=dev)
+        if force_exchange:
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     os.environ["YVB200_PRECISION"] = a.precision
     from yvb200 import lib, ops
     from yvb200.lily_compat import build_lily
@@ -164,12 +167,12 @@ def main():
     model = build_lily(cfg, args, device=dev).train()
     host_batch = [t.pin_memory() if torch.is_tensor(t) else t for t in synth.make_batch(WORKLOAD, seed=1, rank=rank)]
     exchange = None
-    if world > 1:
+    if world > 1 or force_exchange:
         from yvb200.step import GradientExchange
         warm = torch.ones(1, device=dev)
         dist.all_reduce(warm)                       # communicator set-up happens outside any capture
         torch.cuda.synchronize(dev)
-        exchange = GradientExchange(model)          # bucketed NCCL AVG all-reduce overlapped with backward
+        exchange = GradientExchange(model)          # segmented NCCL AVG all-reduce overlapped with backward
     step = GraphedStep(model, args, host_batch, use_graph=not a.no_graph, exchange=exchange)
 
     def allreduce():
@@ -222,8 +225,15 @@ def main():
     final_loss = float(loss_host[0])
 
     t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    exchange_check = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # after the exchange every rank must hold the same averaged gradients (ranks see different batches)
+        ps = [p for p in model.parameters() if p.grad is not None]
+        chk = torch.stack([p.grad.double().abs().sum() for p in ps[:: max(1, len(ps) // 64)]])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        exchange_check = float(max(((c - allc[0]).abs() / allc[0].clamp_min(1e-30)).max() for c in allc))
     t_dev, t_e2e = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:
@@ -293,7 +303,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / a.steps * 1e3},
             "gpu_launches": step.launches_per_step * a.steps, "gpu_launches_per_step": step.launches_per_step,
             "cuda_graph": not a.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_ops_on_gpu": torch_gpu,
+            "torch_ops_on_gpu": torch_gpu, "exchange_max_rank_mismatch": exchange_check,
             "train_tflops_algorithmic": value * TRAIN_GFLOP_PER_PAIR / 1e3, "final_loss": final_loss}
     print(json.dumps(line))
     if world > 1:

@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the N>1 path.  (a) GradientExchange (bucketed overlapped all-reduce used by
+"""CPU, world_size 2 over gloo: the N>1 path.  (a) GradientExchange (segmented overlapped all-reduce used by
 bench.py / GraphedStep) averages exactly like a plain all-reduce; (b) the drop-in under the reference's own
 wrapper DistributedDataParallel(find_unused_parameters=True) (utils/distributed.py:97-99) reproduces the
 single-process gradient of the concatenated batch."""
@@ -45,11 +45,13 @@ def _worker(rank, world, port, q):
 
     # (a) bucketed exchange, tiny buckets so several collectives are issued
     m1 = build_lily(cfg, args).eval()
-    ex = GradientExchange(m1, bucket_mb=0.05)
+    ex = GradientExchange(m1, segment_mb=0.05)
     m1.zero_grad()
     out = m1(*synth.model_inputs(batches[rank]))
+    ex.begin()
     losses.total_loss(losses.step_losses(batches[rank], out, args, True), args).backward()
-    ex.finish()
+    ex.end()
+    ex.exchange()
     err_a = max(float((p.grad - want[n]).abs().max() / (want[n].abs().max() + 1e-12))
                 for n, p in m1.named_parameters() if p.grad is not None)
     n_buckets = ex.launched

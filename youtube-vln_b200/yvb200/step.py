@@ -18,66 +18,96 @@ _FLOAT_FIELDS = (1, 2, 4)          # image_features, image_locations, image_targ
 class GradientExchange:
     """Data-parallel gradient averaging overlapped with backward.
 
-    A post-accumulate hook on every parameter collects finished gradients into ~``bucket_mb`` buckets; a full
-    bucket is all-reduced (NCCL ``AVG``, one grouped launch for all its tensors) on a communication stream that
-    only waits for the backward work issued so far.  Under ``torch.cuda.graph`` capture the collectives become
-    graph nodes on a parallel branch, so every replay overlaps them with the remaining backward kernels.  The
-    reference gets the same effect from ``DistributedDataParallel`` bucket hooks (utils/distributed.py:97-99).
+    A post-accumulate hook on every parameter collects finished gradients; every ``segment_mb`` of them closes a
+    *segment*: the stream is joined with the helper streams and an **external** CUDA event is recorded (inside a
+    captured step this is an event-record node of the graph).  After the step is launched, the communication stream
+    waits for each segment's event in turn and all-reduces that segment (NCCL ``AVG``, one grouped launch per
+    segment) while the rest of the backward graph is still executing.  NCCL itself stays outside the graph.
+    The reference gets the same overlap from ``DistributedDataParallel`` bucket hooks (utils/distributed.py:97-99).
     """
 
-    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 64.0):
+    def __init__(self, model: torch.nn.Module, group=None, segment_mb: float = 160.0, overlap: bool = True):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group)
-        self.bucket_bytes = int(bucket_mb * 2 ** 20)
-        self.pending: List[torch.Tensor] = []
-        self.pending_bytes = 0
+        self.segment_bytes = int(segment_mb * 2 ** 20)
+        self.overlap = overlap
         self.device = next(model.parameters()).device
-        self.comm = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
-        self.avg = dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.nccl = dist.get_backend(group) == "nccl"
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
                         if p.requires_grad]
+        self.recording = False
+        self.segments = []          # [(event or None, [grads])] of the step being issued / captured
+        self.pending: List[torch.Tensor] = []
+        self.pending_bytes = 0
         self.launched = 0
-        self.defer = False          # True: hooks do nothing, ``reduce_all`` exchanges every gradient after backward
 
-    def reduce_all(self, model: torch.nn.Module):
-        """Bucketed exchange of all gradients (used when the collectives are not part of a captured graph)."""
-        for p in model.parameters():
-            if p.grad is not None:
-                self.pending.append(p.grad)
-                self.pending_bytes += p.grad.numel() * p.grad.element_size()
-                if self.pending_bytes >= self.bucket_bytes:
-                    self._flush()
-        self.finish()
+    # ---- called while the step is being issued (eagerly or under capture)
+    def begin(self):
+        self.recording = True
+        self.segments, self.pending, self.pending_bytes = [], [], 0
 
     def _on_grad(self, p: torch.Tensor):
-        g = p.grad
-        if g is None or self.defer:
+        if not self.recording or p.grad is None:
             return
-        self.pending.append(g)
-        self.pending_bytes += g.numel() * g.element_size()
-        if self.pending_bytes >= self.bucket_bytes:
-            self._flush()
+        self.pending.append(p.grad)
+        self.pending_bytes += p.grad.numel() * p.grad.element_size()
+        if self.overlap and self.pending_bytes >= self.segment_bytes:
+            self._close_segment(with_event=True)
 
-    def _flush(self):
+    def _close_segment(self, with_event: bool):
         if not self.pending:
             return
-        grads, self.pending, self.pending_bytes = self.pending, [], 0
-        if self.comm is not None:
+        ev = None
+        if with_event and self.cuda:
+            from . import ops
+            r = ops.rt(self.device)
             cur = torch.cuda.current_stream(self.device)
-            self.comm.wait_stream(cur)
-            with torch.cuda.stream(self.comm):
-                self._reduce(grads)
+            capturing = torch.cuda.is_current_stream_capturing()
+            for s_ in [r.branch_stream] + list(r._helpers.values()):
+                if s_ == cur:
+                    continue
+                if capturing:                                 # only streams that belong to this capture can be joined
+                    with torch.cuda.stream(s_):
+                        if not torch.cuda.is_current_stream_capturing():
+                            continue
+                cur.wait_stream(s_)                           # everything issued so far precedes the event
+            ev = torch.cuda.Event(external=True)
+            ev.record(cur)
+        self.segments.append((ev, self.pending))
+        self.pending, self.pending_bytes = [], 0
+
+    def end(self):
+        """Close the last segment (it is covered by the completion of the step itself)."""
+        self._close_segment(with_event=False)
+        self.recording = False
+
+    # ---- called after the step has been launched (after graph.replay() or the eager body)
+    def exchange(self):
+        if self.cuda:
+            main = torch.cuda.current_stream(self.device)
+            for ev, grads in self.segments:
+                if ev is not None:
+                    self.comm.wait_event(ev)
+                else:
+                    self.comm.wait_stream(main)
+                with torch.cuda.stream(self.comm):
+                    self._reduce(grads)
+                self.launched += 1
+            main.wait_stream(self.comm)
         else:
-            self._reduce(grads)
-        self.launched += 1
+            for _, grads in self.segments:
+                self._reduce(grads)
+                self.launched += 1
 
     def _reduce(self, grads):
         dist = self.dist
-        if self.avg == dist.ReduceOp.AVG:           # NCCL: one grouped launch, averaging inside the collective
+        if self.nccl:                               # one grouped launch, averaging inside the collective
             with dist._coalescing_manager(group=self.group, device=self.device, async_ops=False):
                 for g in grads:
-                    dist.all_reduce(g, op=self.avg, group=self.group)
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             return
         flat = torch.cat([g.reshape(-1) for g in grads])        # gloo (CPU tests): flatten, sum, scatter back
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -87,11 +117,100 @@ class GradientExchange:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
 
-    def finish(self):
-        """Reduce the last partial bucket and make the current stream wait for all communication."""
-        self._flush()
-        if self.comm is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
+class GraphedStep:
+    def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
+                 refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
+        self.model, self.args = model, args
+        self.exchange = exchange
+        self.device = next(model.parameters()).device
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
+                        if p.requires_grad]
+        self.recording = False
+        self.segments = []          # [(event or None, [grads])] of the step being issued / captured
+        self.pending: List[torch.Tensor] = []
+        self.pending_bytes = 0
+        self.launched = 0
+
+    # ---- called while the step is being issued (eagerly or under capture)
+    def begin(self):
+        self.recording = True
+        self.segments, self.pending, self.pending_bytes = [], [], 0
+
+    def _on_grad(self, p: torch.Tensor):
+        if not self.recording or p.grad is None:
+            return
+        self.pending.append(p.grad)
+        self.pending_bytes += p.grad.numel() * p.grad.element_size()
+        if self.overlap and self.pending_bytes >= self.segment_bytes:
+            self._close_segment(with_event=True)
+
+    def _close_segment(self, with_event: bool):
+        if not self.pending:
+            return
+        ev = None
+        if with_event and self.cuda:
+            from . import ops
+            r = ops.rt(self.device)
+            cur = torch.cuda.current_stream(self.device)
+            capturing = torch.cuda.is_current_stream_capturing()
+            for s_ in [r.branch_stream] + list(r._helpers.values()):
+                if s_ == cur:
+                    continue
+                if capturing:                                 # only streams that belong to this capture can be joined
+                    with torch.cuda.stream(s_):
+                        if not torch.cuda.is_current_stream_capturing():
+                            continue
+                cur.wait_stream(s_)                           # everything issued so far precedes the event
+            ev = torch.cuda.Event(external=True)
+            ev.record(cur)
+        self.segments.append((ev, self.pending))
+        self.pending, self.pending_bytes = [], 0
+
+    def end(self):
+        """Close the last segment (it is covered by the completion of the step itself)."""
+        self._close_segment(with_event=False)
+        self.recording = False
+
+    # ---- called after the step has been launched (after graph.replay() or the eager body)
+    def exchange(self):
+        if self.cuda:
+            main = torch.cuda.current_stream(self.device)
+            for ev, grads in self.segments:
+                if ev is not None:
+                    self.comm.wait_event(ev)
+                else:
+                    self.comm.wait_stream(main)
+                with torch.cuda.stream(self.comm):
+                    self._reduce(grads)
+                self.launched += 1
+            main.wait_stream(self.comm)
+        else:
+            for _, grads in self.segments:
+                self._reduce(grads)
+                self.launched += 1
+
+    def _reduce(self, grads):
+        dist = self.dist
+        if self.nccl:                               # one grouped launch, averaging inside the collective
+            with dist._coalescing_manager(group=self.group, device=self.device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])        # gloo (CPU tests): flatten, sum, scatter back
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(float(self.world))
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def remove(self):
         for h in self.handles:
@@ -132,8 +251,7 @@ class GraphedStep:
             self._zero_grads()
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.launch_count()
-            mode = "thread_local" if self.capture_exchange else "global"
-            with torch.cuda.graph(self.graph, capture_error_mode=mode):
+            with torch.cuda.graph(self.graph):
                 self._body()
             self.launches_per_step = lib.launch_count() - n0
         else:
@@ -162,9 +280,11 @@ class GraphedStep:
                 tot = tot + ld[k]
         if "traj" in ld:
             tot = tot + self.args.traj_loss_scale * ld["traj"]
+        if self.exchange is not None:
+            self.exchange.begin()
         tot.backward()
-        if self.exchange is not None and self.capture_exchange:
-            self.exchange.finish()
+        if self.exchange is not None:
+            self.exchange.end()
         self.loss = tot.detach()
 
     def load(self, batch: List[torch.Tensor]):
@@ -183,6 +303,6 @@ class GraphedStep:
         else:
             self._zero_grads()
             self._body()
-        if self.exchange is not None and not self.capture_exchange:
-            self.exchange.reduce_all(self.model)
+        if self.exchange is not None:
+            self.exchange.exchange()
         return self.loss
