@@ -25,8 +25,18 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
+// This file is compiled twice (see Makefile):
+//   YV_BLOCK_K=64 -> yv_gemm_k64: persistent, one CTA per SM, 192 KB operand ring + dedicated epilogue staging.
+//                    Best when a launch has several tiles per SM (epilogue of tile i overlaps main loop of i+1).
+//   YV_BLOCK_K=32 -> yv_gemm_k32: one tile per CTA, 96 KB ring (epilogue staging reuses it), two CTAs per SM.
+//                    Best for the single-wave problems of the 8-pair step: CTAs of concurrent launches share SMs.
 #ifndef YV_BLOCK_K
-#define YV_BLOCK_K 32
+#define YV_BLOCK_K 64
+#endif
+#if YV_BLOCK_K == 32
+#define YV_GEMM_ENTRY yv_gemm_k32
+#else
+#define YV_GEMM_ENTRY yv_gemm_k64
 #endif
 constexpr int BLOCK_K = YV_BLOCK_K;                           // 32: 64 B rows / 64B swizzle / 2 CTAs per SM; 64: 128B swizzle
 constexpr int KMAJ_LAYOUT = BLOCK_K == 32 ? 4 : 2;            // UMMA layout type of K-major tiles (SWIZZLE_64B / _128B)
@@ -34,21 +44,26 @@ constexpr int KMAJ_SBO = BLOCK_K * 2 * 8;                     // 8 rows of BLOCK
 constexpr int UMMA_K = 16;
 constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 8 KB (A and B tiles have the same size)
 constexpr int NUM_THREADS = 320;                               // TMA warp, MMA warp, 8 epilogue warps
-constexpr int TMEM_COLS = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr bool PERSISTENT = BLOCK_K == 64;
+constexpr int TMEM_COLS = PERSISTENT ? 256 : 128;             // two 128-column f32 accumulators when persistent
+constexpr int EPI_STAGING_BYTES = PERSISTENT ? NUM_EPI_WARPS * 4096 : 0;   // k32: staging reuses the drained ring
 
 template <int PASSES>
 struct Cfg {
     static constexpr int TILES_PER_STAGE = PASSES == 3 ? 4 : 2;   // A_hi, B_hi, (A_lo, B_lo)
     static constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
     static constexpr int STAGES = PASSES == 3 ? 3 : 6;            // 96 KB (BLOCK_K=32) / 192 KB (64) operand ring
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static_assert(STAGES * STAGE_BYTES >= 8 * 4096, "epilogue staging (8 warps x 4 KB) reuses the operand ring");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+    static_assert(PERSISTENT || STAGES * STAGE_BYTES >= NUM_EPI_WARPS * 4096, "k32 staging must fit in the ring");
 };
 
 struct KParams {
     int M, N, K;
     int nb0;
     int splits, kb_per_split;   // split-K (only for un-batched launches with a linear, f32-only epilogue)
+    int total_tiles;            // tiles_m * tiles_n * batch * splits, walked persistently
     int a_mn, b_mn;
     float alpha;
     int act;
@@ -165,32 +180,32 @@ __device__ long long yv_dbg[32];
 #endif
 
 // ------------------------------------------------------------------------------------------- kernel
+// Persistent: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  Two TMEM accumulators
+// (2 x 128 columns) let the epilogue of tile i overlap the TMA/MMA main loop of tile i+1.
 template <int PASSES>
-__global__ void __launch_bounds__(NUM_THREADS, BLOCK_K == 32 ? 2 : 1)
+__global__ void __launch_bounds__(NUM_THREADS, PERSISTENT ? 1 : 2)
 yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const KParams p) {
     using C = Cfg<PASSES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + C::STAGES * C::STAGE_BYTES);
-    // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full; then the TMEM base address word
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 1);
+    // epilogue staging, 8 x 4 KB: after the ring (persistent) or on top of it (one tile per CTA: ring is drained)
+    const uint32_t stage_smem = PERSISTENT ? smem_base + C::STAGES * C::STAGE_BYTES : smem_base;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + C::STAGES * C::STAGE_BYTES + EPI_STAGING_BYTES);
+    // bars: [0,S) full, [S,2S) empty, 2S..2S+1 tmem_full, 2S+2..2S+3 tmem_empty; then the TMEM base address word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BLOCK_M;
-    const int n0 = blockIdx.x * BLOCK_N;
-    const int split = blockIdx.z % p.splits;
-    const int z = blockIdx.z / p.splits;
-    const int b0 = z % p.nb0, b1 = z / p.nb0;
     const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-    const int kb_lo = split * p.kb_per_split;
-    const int num_kb = min(p.kb_per_split, total_kb - kb_lo);   // >= 1 by construction on the host
+    const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
     if (threadIdx.x == 0) YV_T(0);
     yv_pdl_trigger();      // the next kernel may start its own prologue while this one runs
 
@@ -199,7 +214,10 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_b) : "memory");
@@ -217,36 +235,53 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     yv_pdl_wait();         // barriers, TMEM and descriptors are ready: now wait for the producers of our operands
     if (threadIdx.x == 0) YV_T(1);
 
+    // tile -> (split, n block, m block, batch); m varies fastest so concurrently running CTAs share B tiles in L2
+    auto decode = [&](int t, int& m0, int& n0, int& z, int& split) {
+        split = t % p.splits;
+        t /= p.splits;
+        m0 = (t % tiles_m) * BLOCK_M;
+        t /= tiles_m;
+        n0 = (t % tiles_n) * BLOCK_N;
+        z = t / tiles_n;
+    };
+
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
-                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                const int k0 = (kb_lo + kb) * BLOCK_K;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int m0, n0, z, split;
+                decode(tile, m0, n0, z, split);
+                const int b0 = z % p.nb0, b1 = z / p.nb0;
+                const int kb_lo = split * p.kb_per_split;
+                const int num_kb = min(p.kb_per_split, total_kb - kb_lo);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const int k0 = (kb_lo + kb) * BLOCK_K;
 #pragma unroll
-                for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
-                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
-                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
-                    if (!p.a_mn) {
-                        tma_load_5d(sa, &map_a, full_bar(stage), k0, m0, b0, b1, pl);
-                    } else {
-                        tma_load_5d(sa, &map_a, full_bar(stage), m0, k0, b0, b1, pl);
-                        tma_load_5d(sa + TILE_BYTES / 2, &map_a, full_bar(stage), m0 + 64, k0, b0, b1, pl);
+                    for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
+                        const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                        const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                        if (!p.a_mn) {
+                            tma_load_5d(sa, &map_a, full_bar(stage), k0, m0, b0, b1, pl);
+                        } else {
+                            tma_load_5d(sa, &map_a, full_bar(stage), m0, k0, b0, b1, pl);
+                            tma_load_5d(sa + TILE_BYTES / 2, &map_a, full_bar(stage), m0 + 64, k0, b0, b1, pl);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_5d(sb, &map_b, full_bar(stage), k0, n0, b0, b1, pl);
+                        } else {
+                            tma_load_5d(sb, &map_b, full_bar(stage), n0, k0, b0, b1, pl);
+                            tma_load_5d(sb + TILE_BYTES / 2, &map_b, full_bar(stage), n0 + 64, k0, b0, b1, pl);
+                        }
                     }
-                    if (!p.b_mn) {
-                        tma_load_5d(sb, &map_b, full_bar(stage), k0, n0, b0, b1, pl);
-                    } else {
-                        tma_load_5d(sb, &map_b, full_bar(stage), n0, k0, b0, b1, pl);
-                        tma_load_5d(sb + TILE_BYTES / 2, &map_b, full_bar(stage), n0 + 64, k0, b0, b1, pl);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
-                }
-                if (++stage == C::STAGES) {
-                    stage = 0;
-                    phase ^= 1u;
                 }
             }
         }
@@ -261,153 +296,182 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t accum = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(full_bar(stage), phase);
-                if (kb == 0) YV_T(2);
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int split = tile % p.splits;
+                const int kb_lo = split * p.kb_per_split;
+                const int num_kb = min(p.kb_per_split, total_kb - kb_lo);
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);      // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
-                uint64_t da[2], db[2];
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                uint32_t accum = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    if (kb == 0) YV_T(2);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                    uint64_t da[2], db[2];
 #pragma unroll
-                for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
-                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
-                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
-                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, KMAJ_LAYOUT);
-                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, KMAJ_LAYOUT);
-                }
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    if (PASSES == 3) {
-                        // small cross terms first, the dominant hi*hi term last
-                        umma_bf16(tmem_base, da[1] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
-                        accum = 1;
-                        umma_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[1] + (uint64_t)(b_step * k), idesc, 1);
+                    for (int pl = 0; pl < (PASSES == 3 ? 2 : 1); ++pl) {
+                        const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                        const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                        da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, KMAJ_LAYOUT);
+                        db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, KMAJ_LAYOUT);
                     }
-                    umma_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
-                    accum = 1;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        if (PASSES == 3) {
+                            // small cross terms first, the dominant hi*hi term last
+                            umma_bf16(tmem_d, da[1] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                            accum = 1;
+                            umma_bf16(tmem_d, da[0] + (uint64_t)(a_step * k), db[1] + (uint64_t)(b_step * k), idesc, 1);
+                        }
+                        umma_bf16(tmem_d, da[0] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs retire
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
-                umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs retire
-                if (++stage == C::STAGES) {
-                    stage = 0;
-                    phase ^= 1u;
+                YV_T(3);
+                umma_commit(tmem_full_bar(acc));     // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
                 }
             }
-            YV_T(3);
-            umma_commit(tmem_full_bar);          // accumulator complete -> epilogue
         }
     } else {
         // ===================================== epilogue ==========================================
         // 8 warps: two per TMEM lane quarter, each owning 64 of the tile's 128 columns as two 32x32 chunks.
-        // A chunk goes TMEM -> registers (thread = row) -> XOR-swizzled smem (the drained pipeline stage 0)
-        // -> registers (8 lanes = one 128-byte row segment), so every global access below is coalesced.
+        // A chunk goes TMEM -> registers (thread = row) -> XOR-swizzled smem staging -> registers (8 lanes = one
+        // 128-byte row segment), so every global access below is coalesced.
         const int ew = warp - 2;
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int half = ew >> 2;
-        mbar_wait(tmem_full_bar, 0);
-        if (threadIdx.x == 64) YV_T(4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
-        const uint32_t stg = smem_base + (uint32_t)ew * 4096u;
-        const long long obatch = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1;
-        const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
+        const uint32_t stg = stage_smem + (uint32_t)ew * 4096u;
         const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.out_sb0 & 3) == 0) && ((p.out_sb1 & 3) == 0) &&
                             ((p.ld_pl & 3) == 0) && ((p.pl_sb0 & 3) == 0) && ((p.pl_sb1 & 3) == 0) &&
                             ((p.pl_plane_stride & 3) == 0) &&
                             (((uintptr_t)p.out32 | (uintptr_t)p.aux_out | (uintptr_t)p.aux_in | (uintptr_t)p.residual |
                               (uintptr_t)p.bias) & 15) == 0 && (((uintptr_t)p.out_planes) & 7) == 0;
         const int cg = lane & 7;                             // float4 column group of this lane inside a chunk
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int m0, n0, z, split;
+            decode(tile, m0, n0, z, split);
+            const int b0 = z % p.nb0, b1 = z / p.nb0;
+            const long long obatch = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1;
+            const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            if (threadIdx.x == 64) YV_T(4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = half * 2 + cc;
-            const int nc = n0 + c * 32;
-            if (nc >= p.N) break;                            // warp-uniform
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;
+                const int nc = n0 + c * 32;
+                if (nc >= p.N) break;                            // warp-uniform
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), raw);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(raw[4 * g]), "r"(raw[4 * g + 1]),
-                             "r"(raw[4 * g + 2]), "r"(raw[4 * g + 3])
-                             : "memory");
-            }
-            __syncwarp();
-            const int n = nc + 4 * cg;
-            const bool quad_ok = vec_ok && (n + 3 < p.N);
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && quad_ok && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                for (int g = 0; g < 8; ++g) {
+                    const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(raw[4 * g]), "r"(raw[4 * g + 1]),
+                                 "r"(raw[4 * g + 2]), "r"(raw[4 * g + 3])
+                                 : "memory");
+                }
+                __syncwarp();
+                const int n = nc + 4 * cg;
+                const bool quad_ok = vec_ok && (n + 3 < p.N);
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && quad_ok && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-                const int r = (lane >> 3) + 4 * i;
-                const int row = m0 + q * 32 + r;
-                float4 v;
-                {
-                    const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((cg ^ (r & 7)) * 16);
-                    uint32_t x0, x1, x2, x3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
-                    v = make_float4(__uint_as_float(x0), __uint_as_float(x1), __uint_as_float(x2), __uint_as_float(x3));
-                }
-                if (row >= p.M || n >= p.N) continue;
-                const long long ob = obatch + (long long)row * p.ld_out + n;
-                const long long pb = pbatch + (long long)row * p.ld_pl + n;
-                if (!quad_ok) {                              // ragged edge / unaligned leading dimension
-                    epilogue_scalar(p, drop, v.x, n, z, row, ob - n, pb - n);
-                    epilogue_scalar(p, drop, v.y, n + 1, z, row, ob - n, pb - n);
-                    epilogue_scalar(p, drop, v.z, n + 2, z, row, ob - n, pb - n);
-                    epilogue_scalar(p, drop, v.w, n + 3, z, row, ob - n, pb - n);
-                    continue;
-                }
-                v.x = p.alpha * v.x + bias4.x; v.y = p.alpha * v.y + bias4.y;
-                v.z = p.alpha * v.z + bias4.z; v.w = p.alpha * v.w + bias4.w;
-                if (p.splits > 1) {
-                    // split-K: partial sums meet in a zero-initialised f32 output through vector reductions; the
-                    // epilogue is linear here (bias and residual come from split 0, dropout scales every partial)
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (lane >> 3) + 4 * i;
+                    const int row = m0 + q * 32 + r;
+                    float4 v;
+                    {
+                        const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((cg ^ (r & 7)) * 16);
+                        uint32_t x0, x1, x2, x3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                        v = make_float4(__uint_as_float(x0), __uint_as_float(x1), __uint_as_float(x2), __uint_as_float(x3));
+                    }
+                    if (row >= p.M || n >= p.N) continue;
+                    const long long ob = obatch + (long long)row * p.ld_out + n;
+                    const long long pb = pbatch + (long long)row * p.ld_pl + n;
+                    if (!quad_ok) {                              // ragged edge / unaligned leading dimension
+                        epilogue_scalar(p, drop, v.x, n, z, row, ob - n, pb - n);
+                        epilogue_scalar(p, drop, v.y, n + 1, z, row, ob - n, pb - n);
+                        epilogue_scalar(p, drop, v.z, n + 2, z, row, ob - n, pb - n);
+                        epilogue_scalar(p, drop, v.w, n + 3, z, row, ob - n, pb - n);
+                        continue;
+                    }
+                    v.x = p.alpha * v.x + bias4.x; v.y = p.alpha * v.y + bias4.y;
+                    v.z = p.alpha * v.z + bias4.z; v.w = p.alpha * v.w + bias4.w;
+                    if (p.splits > 1) {
+                        // split-K: partial sums meet in a zero-initialised f32 output through vector reductions; the
+                        // epilogue is linear here (bias and residual come from split 0, dropout scales every partial)
+                        if (drop.thresh) {
+                            const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
+                            v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
+                            v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
+                        }
+                        if (p.residual && split == 0) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out32 + ob), "f"(v.x), "f"(v.y),
+                                     "f"(v.z), "f"(v.w)
+                                     : "memory");
+                        continue;
+                    }
+                    if (p.aux_out) *reinterpret_cast<float4*>(p.aux_out + ob) = v;
+                    if (p.act == YV_ACT_GELU) {
+                        v.x = yv_gelu(v.x); v.y = yv_gelu(v.y); v.z = yv_gelu(v.z); v.w = yv_gelu(v.w);
+                    } else if (p.act == YV_ACT_RELU) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
                     if (drop.thresh) {
                         const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
                         v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
                         v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
                     }
-                    if (p.residual && split == 0) {
+                    if (p.act == YV_ACT_MUL_GELU_GRAD) {
+                        const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
+                        v.x *= yv_gelu_grad(t.x); v.y *= yv_gelu_grad(t.y); v.z *= yv_gelu_grad(t.z); v.w *= yv_gelu_grad(t.w);
+                    } else if (p.act == YV_ACT_MUL_RELU_MASK) {
+                        const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
+                        v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
+                        v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+                    }
+                    if (p.residual) {
                         const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
                         v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                     }
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out32 + ob), "f"(v.x), "f"(v.y),
-                                 "f"(v.z), "f"(v.w)
-                                 : "memory");
-                    continue;
+                    if (p.out32) *reinterpret_cast<float4*>(p.out32 + ob) = v;
+                    if (p.out_planes) {
+                        __align__(8) __nv_bfloat16 h4[4], l4[4];
+                        yv_split(v.x, h4[0], l4[0]); yv_split(v.y, h4[1], l4[1]);
+                        yv_split(v.z, h4[2], l4[2]); yv_split(v.w, h4[3], l4[3]);
+                        *reinterpret_cast<uint2*>(p.out_planes + pb) = *reinterpret_cast<uint2*>(h4);
+                        *reinterpret_cast<uint2*>(p.out_planes + pb + p.pl_plane_stride) = *reinterpret_cast<uint2*>(l4);
+                    }
                 }
-                if (p.aux_out) *reinterpret_cast<float4*>(p.aux_out + ob) = v;
-                if (p.act == YV_ACT_GELU) {
-                    v.x = yv_gelu(v.x); v.y = yv_gelu(v.y); v.z = yv_gelu(v.z); v.w = yv_gelu(v.w);
-                } else if (p.act == YV_ACT_RELU) {
-                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                if (drop.thresh) {
-                    const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
-                    v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
-                    v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
-                }
-                if (p.act == YV_ACT_MUL_GELU_GRAD) {
-                    const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
-                    v.x *= yv_gelu_grad(t.x); v.y *= yv_gelu_grad(t.y); v.z *= yv_gelu_grad(t.z); v.w *= yv_gelu_grad(t.w);
-                } else if (p.act == YV_ACT_MUL_RELU_MASK) {
-                    const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
-                    v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
-                    v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-                }
-                if (p.residual) {
-                    const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
-                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                }
-                if (p.out32) *reinterpret_cast<float4*>(p.out32 + ob) = v;
-                if (p.out_planes) {
-                    __align__(8) __nv_bfloat16 h4[4], l4[4];
-                    yv_split(v.x, h4[0], l4[0]); yv_split(v.y, h4[1], l4[1]);
-                    yv_split(v.z, h4[2], l4[2]); yv_split(v.w, h4[3], l4[3]);
-                    *reinterpret_cast<uint2*>(p.out_planes + pb) = *reinterpret_cast<uint2*>(h4);
-                    *reinterpret_cast<uint2*>(p.out_planes + pb + p.pl_plane_stride) = *reinterpret_cast<uint2*>(l4);
-                }
+                __syncwarp();                                    // staging buffer is reused by the next chunk
             }
-            __syncwarp();                                    // staging buffer is reused by the next chunk
+            // this warp has finished reading its TMEM lanes of accumulator `acc`: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty_bar(acc)) : "memory");
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
         }
     }
 
@@ -471,7 +535,7 @@ int make_map(CUtensorMap* map, const YvOperand& o, int passes, const char* which
 
 void yv_count_launch();
 
-extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
+extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
     YV_CHECK(g != nullptr, "yv_gemm: NULL args");
     YV_CHECK(g->passes == 1 || g->passes == 3, "yv_gemm: passes must be 1 or 3 (got %d)", g->passes);
     YV_CHECK(g->M > 0 && g->N > 0 && g->K > 0, "yv_gemm: empty problem M=%d N=%d K=%d", g->M, g->N, g->K);
@@ -529,8 +593,16 @@ extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
             p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
         }
     }
-    dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, (unsigned)(a.nb0 * a.nb1 * p.splits));
-    YV_CHECK(grid.y <= 65535 && grid.z <= 65535, "yv_gemm: grid too large");
+    const long long total_tiles = (long long)tiles * a.nb0 * a.nb1 * p.splits;
+    YV_CHECK(total_tiles < 2147483647LL, "yv_gemm: too many tiles");
+    p.total_tiles = (int)total_tiles;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        YV_CUDA(cudaGetDevice(&dev));
+        YV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    dim3 grid((unsigned)((!PERSISTENT || total_tiles < num_sms) ? total_tiles : num_sms), 1, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p.splits > 1)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
