@@ -288,6 +288,27 @@ def main():
     except Exception as e:  # informational only
         torch_gpu = {"error": repr(e)[:200]}
 
+    # optimizer step, reported separately from the metric: fused multi-tensor AdamW over all gradients
+    optim_ms = None
+    try:
+        from yvb200.optim import FusedAdamW
+        nd = ("bias", "LayerNorm.weight", "LayerNorm.bias")
+        named = list(model.named_parameters())
+        opt = FusedAdamW([{"params": [p for n, p in named if any(x in n for x in nd)], "weight_decay": 0.0},
+                          {"params": [p for n, p in named if not any(x in n for x in nd)], "weight_decay": 0.01}], lr=4e-5)
+        for _ in range(2):
+            opt.step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        optim_ms = e0.elapsed_time(e1) / 5
+    except Exception as e:  # informational only
+        optim_ms = repr(e)[:200]
+
     cpu = None
     if not a.no_cpu_baseline:
         v, sec, cores = run_cpu_oracle(2, 1)
@@ -303,7 +324,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / a.steps * 1e3},
             "gpu_launches": step.launches_per_step * a.steps, "gpu_launches_per_step": step.launches_per_step,
             "cuda_graph": not a.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "torch_ops_on_gpu": torch_gpu, "exchange_max_rank_mismatch": exchange_check,
+            "torch_ops_on_gpu": torch_gpu, "fused_adamw_ms_per_step": optim_ms, "exchange_max_rank_mismatch": exchange_check,
             "train_tflops_algorithmic": value * TRAIN_GFLOP_PER_PAIR / 1e3, "final_loss": final_loss}
     print(json.dumps(line))
     if world > 1:

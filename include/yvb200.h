@@ -82,6 +82,27 @@ typedef struct {
 int yv_split_multi(const YvSplitSeg* segs_dev, int32_t nseg, int64_t total_blocks, void* planes,
                    int64_t plane_stride, yv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW -- SURVEY.md 8(f) "next" #1; replaces the per-parameter Python loop of
+ * vilbert/optimization.py:141-187 (bias-corrected Adam, eps added after sqrt(v), decoupled decay applied to the
+ * updated weight).  hyper_dev = {lr, step_size, beta1, beta2, eps, 1-beta1, 1-beta2}.  Segments with plane pointers also get the
+ * updated weight re-split into bf16 hi/lo planes (saves the per-step yv_split_multi pass).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    void* plane_hi;      /* NULL for parameters that are not GEMM operands */
+    void* plane_lo;
+    int64_t numel;
+    int64_t first_blk;   /* prefix sum of ceil(numel / 2048) */
+    float weight_decay;
+    int32_t _pad;
+} YvAdamSeg;
+int yv_adamw_multi(const YvAdamSeg* segs_dev, int32_t nseg, int64_t total_blocks, const float* hyper_dev,
+                   yv_stream_t stream);
+
 /* dropout RNG state {seed, step}: step += 1 (captured once per training step) */
 int yv_rng_advance(uint64_t* rng, yv_stream_t stream);
 

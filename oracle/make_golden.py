@@ -100,6 +100,44 @@ def run(workload: str):
           f"ref fwd+bwd {dt:.1f}s -> {path} ({os.path.getsize(path)/1e3:.0f} KB)")
 
 
+def run_adamw():
+    """3 steps of the reference's own AdamW (vilbert/optimization.py:107) with the reference's param grouping
+    (vilbert/vilbert_init.py:9-18) on a handful of named tensors and seeded gradients."""
+    import importlib
+    refload.load_reference()
+    sys.path.insert(0, refload.REFERENCE_ROOT)
+    opt = importlib.import_module("vilbert.optimization")
+    sys.path.remove(refload.REFERENCE_ROOT)
+    names = {"enc.dense.weight": (48, 40), "enc.dense.bias": (48,), "enc.LayerNorm.weight": (48,),
+             "enc.LayerNorm.bias": (48,), "emb.word_embeddings.weight": (37, 24)}
+    g = torch.Generator().manual_seed(123)
+    params = {n: torch.nn.Parameter(torch.randn(s, generator=g) * 0.05) for n, s in names.items()}
+    groups = [{"params": [], "weight_decay": 0.0}, {"params": [], "weight_decay": 0.01}]
+    for n, p_ in params.items():
+        groups[0 if any(nd in n for nd in ("bias", "LayerNorm.weight", "LayerNorm.bias")) else 1]["params"].append(p_)
+    optim = opt.AdamW(groups, lr=4e-5)
+    out = {}
+    for n, p_ in params.items():
+        out["p0/" + n] = p_.detach().numpy().copy()
+    lrs = [4e-5, 3e-5, 2.5e-5]
+    for step in range(3):
+        for grp in optim.param_groups:
+            grp["lr"] = lrs[step]
+        for n, p_ in params.items():
+            p_.grad = torch.randn(p_.shape, generator=g) * (0.01 if step != 1 else 1e-4)
+            out[f"g{step}/" + n] = p_.grad.numpy().copy()
+        optim.step()
+        for n, p_ in params.items():
+            out[f"p{step + 1}/" + n] = p_.detach().numpy().copy()
+    for n, p_ in params.items():
+        out["m3/" + n] = optim.state[p_]["exp_avg"].numpy().copy()
+        out["v3/" + n] = optim.state[p_]["exp_avg_sq"].numpy().copy()
+    out["lrs"] = np.array(lrs)
+    path = os.path.join(ROOT, "tests", "golden", "adamw.npz")
+    np.savez_compressed(path, **out)
+    print("adamw golden ->", path)
+
+
 if __name__ == "__main__":
-    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2"]):
-        run(wl)
+    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw"]):
+        run_adamw() if wl == "adamw" else run(wl)

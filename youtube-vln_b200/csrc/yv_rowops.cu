@@ -82,6 +82,73 @@ __global__ void split_multi_kernel(const YvSplitSeg* __restrict__ segs, int nseg
     }
 }
 
+// Fused multi-tensor AdamW (vilbert/optimization.py:141-187): one launch updates p / exp_avg / exp_avg_sq of every
+// parameter and, for GEMM weights, re-splits the new value into the bf16 hi/lo planes the next forward reads.
+// hyper = {lr, step_size (= lr * sqrt(1 - b2^t) / (1 - b1^t) or lr), beta1, beta2, eps, 1-beta1, 1-beta2}
+constexpr int ADAM_BLK = 2048;
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const YvAdamSeg* __restrict__ segs, int nseg, const float* __restrict__ hyper) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const long long blk = blockIdx.x;
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].first_blk <= blk) lo = mid; else hi = mid - 1;
+    }
+    const YvAdamSeg s = segs[lo];
+    const float lr = hyper[0], step_size = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4];
+    const float omb1 = hyper[5], omb2 = hyper[6];   // 1-beta rounded from double on the host, as the reference does
+    const float decay = lr * s.weight_decay;
+    const long long base = (blk - s.first_blk) * ADAM_BLK;
+    const long long n = min((long long)ADAM_BLK, s.numel - base);
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(s.plane_hi);
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(s.plane_lo);
+    auto update = [&](float g, float& m, float& v, float& w) {
+        m = m * b1 + omb1 * g;
+        v = v * b2 + omb2 * (g * g);
+        w = w - step_size * (m / (sqrtf(v) + eps));
+        if (s.weight_decay > 0.f) w = w - decay * w;
+    };
+    const bool vec = (((uintptr_t)(s.p + base) | (uintptr_t)(s.g + base) | (uintptr_t)(s.m + base) | (uintptr_t)(s.v + base)) & 15) == 0 &&
+                     (ph == nullptr || ((((uintptr_t)(ph + base) | (uintptr_t)(pl + base)) & 7) == 0));
+    const long long n4 = vec ? (n >> 2) : 0;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+        const long long j = base + 4 * i;
+        const float4 g4 = *reinterpret_cast<const float4*>(s.g + j);
+        float4 m4 = *reinterpret_cast<float4*>(s.m + j);
+        float4 v4 = *reinterpret_cast<float4*>(s.v + j);
+        float4 w4 = *reinterpret_cast<float4*>(s.p + j);
+        update(g4.x, m4.x, v4.x, w4.x);
+        update(g4.y, m4.y, v4.y, w4.y);
+        update(g4.z, m4.z, v4.z, w4.z);
+        update(g4.w, m4.w, v4.w, w4.w);
+        *reinterpret_cast<float4*>(s.m + j) = m4;
+        *reinterpret_cast<float4*>(s.v + j) = v4;
+        *reinterpret_cast<float4*>(s.p + j) = w4;
+        if (ph) {
+            __align__(8) __nv_bfloat16 h[4], l[4];
+            yv_split(w4.x, h[0], l[0]); yv_split(w4.y, h[1], l[1]); yv_split(w4.z, h[2], l[2]); yv_split(w4.w, h[3], l[3]);
+            *reinterpret_cast<uint2*>(ph + j) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(pl + j) = *reinterpret_cast<uint2*>(l);
+        }
+    }
+    for (long long i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+        const long long j = base + i;
+        float m = s.m[j], v = s.v[j], w = s.p[j];
+        update(s.g[j], m, v, w);
+        s.m[j] = m;
+        s.v[j] = v;
+        s.p[j] = w;
+        if (ph) {
+            __nv_bfloat16 h, l;
+            yv_split(w, h, l);
+            ph[j] = h;
+            pl[j] = l;
+        }
+    }
+}
+
 __global__ void rng_advance_kernel(unsigned long long* rng) {
     yv_pdl_trigger();
     yv_pdl_wait(); rng[1] += 1ULL; }
@@ -734,6 +801,14 @@ extern "C" int yv_split_multi(const YvSplitSeg* segs_dev, int32_t nseg, int64_t 
     YV_CHECK(total_blocks < 2147483647LL, "yv_split_multi: too many blocks");
     YV_CUDA(yv_launch(split_multi_kernel, dim3((unsigned)total_blocks), dim3(256), 0, S(stream), segs_dev, nseg,
                                                                       reinterpret_cast<__nv_bfloat16*>(planes), plane_stride));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_adamw_multi(const YvAdamSeg* segs_dev, int32_t nseg, int64_t total_blocks, const float* hyper_dev,
+                              yv_stream_t stream) {
+    YV_CHECK(segs_dev && hyper_dev && nseg > 0 && total_blocks > 0, "yv_adamw_multi: bad arguments");
+    YV_CHECK(total_blocks < 2147483647LL, "yv_adamw_multi: too many blocks");
+    YV_CUDA(yv_launch(adamw_multi_kernel, dim3((unsigned)total_blocks), dim3(256), 0, S(stream), segs_dev, nseg, hyper_dev));
     YV_LAUNCHED();
 }
 

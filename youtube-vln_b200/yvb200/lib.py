@@ -22,7 +22,7 @@ SYMBOLS = [
     "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_split_planes", "yv_split_multi",
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
-    "yv_colsum_planes", "yv_act_bwd_split", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
+    "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
 ]
 
 
@@ -168,6 +168,11 @@ def split_planes(src: torch.Tensor, dst: Optional[Planes] = None) -> Planes:
 def split_multi(segs_dev: torch.Tensor, nseg: int, total_blocks: int, planes: torch.Tensor, plane_stride: int):
     _check(load().yv_split_multi(C.c_void_p(segs_dev.data_ptr()), C.c_int32(nseg), C.c_int64(total_blocks),
                                  C.c_void_p(planes.data_ptr()), C.c_int64(plane_stride), _stream()), "split_multi")
+
+
+def adamw_multi(segs_dev: torch.Tensor, nseg: int, total_blocks: int, hyper_dev: torch.Tensor):
+    _check(load().yv_adamw_multi(C.c_void_p(segs_dev.data_ptr()), C.c_int32(nseg), C.c_int64(total_blocks),
+                                 C.c_void_p(hyper_dev.data_ptr()), _stream()), "adamw_multi")
 
 
 def rng_advance(rng: torch.Tensor):
