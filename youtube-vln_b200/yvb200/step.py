@@ -127,101 +127,6 @@ class GraphedStep:
                  refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
         self.model, self.args = model, args
         self.exchange = exchange
-        self.device = next(model.parameters()).device
-        self.cuda = self.device.type == "cuda"
-        self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
-        self.nccl = dist.get_backend(group) == "nccl"
-        self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
-                        if p.requires_grad]
-        self.recording = False
-        self.segments = []          # [(event or None, [grads])] of the step being issued / captured
-        self.pending: List[torch.Tensor] = []
-        self.pending_bytes = 0
-        self.launched = 0
-
-    # ---- called while the step is being issued (eagerly or under capture)
-    def begin(self):
-        self.recording = True
-        self.segments, self.pending, self.pending_bytes = [], [], 0
-
-    def _on_grad(self, p: torch.Tensor):
-        if not self.recording or p.grad is None:
-            return
-        self.pending.append(p.grad)
-        self.pending_bytes += p.grad.numel() * p.grad.element_size()
-        if self.overlap and self.pending_bytes >= self.segment_bytes:
-            self._close_segment(with_event=True)
-
-    def _close_segment(self, with_event: bool):
-        if not self.pending:
-            return
-        ev = None
-        if with_event and self.cuda:
-            from . import ops
-            r = ops.rt(self.device)
-            cur = torch.cuda.current_stream(self.device)
-            capturing = torch.cuda.is_current_stream_capturing()
-            for s_ in [r.branch_stream] + list(r._helpers.values()):
-                if s_ == cur:
-                    continue
-                if capturing:                                 # only streams that belong to this capture can be joined
-                    with torch.cuda.stream(s_):
-                        if not torch.cuda.is_current_stream_capturing():
-                            continue
-                cur.wait_stream(s_)                           # everything issued so far precedes the event
-            ev = torch.cuda.Event(external=True)
-            ev.record(cur)
-        self.segments.append((ev, self.pending))
-        self.pending, self.pending_bytes = [], 0
-
-    def end(self):
-        """Close the last segment (it is covered by the completion of the step itself)."""
-        self._close_segment(with_event=False)
-        self.recording = False
-
-    # ---- called after the step has been launched (after graph.replay() or the eager body)
-    def exchange(self):
-        if self.cuda:
-            main = torch.cuda.current_stream(self.device)
-            for ev, grads in self.segments:
-                if ev is not None:
-                    self.comm.wait_event(ev)
-                else:
-                    self.comm.wait_stream(main)
-                with torch.cuda.stream(self.comm):
-                    self._reduce(grads)
-                self.launched += 1
-            main.wait_stream(self.comm)
-        else:
-            for _, grads in self.segments:
-                self._reduce(grads)
-                self.launched += 1
-
-    def _reduce(self, grads):
-        dist = self.dist
-        if self.nccl:                               # one grouped launch, averaging inside the collective
-            with dist._coalescing_manager(group=self.group, device=self.device, async_ops=False):
-                for g in grads:
-                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
-            return
-        flat = torch.cat([g.reshape(-1) for g in grads])        # gloo (CPU tests): flatten, sum, scatter back
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(float(self.world))
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
-
-    def remove(self):
-        for h in self.handles:
-            h.remove()
-
-
-class GraphedStep:
-    def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
-                 refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
-        self.model, self.args = model, args
-        self.exchange = exchange
         # NCCL collectives inside the captured graph overlap the exchange with backward; opt-in because a capture
         # with live communicator threads needs thread-local capture mode (YVB200_CAPTURE_NCCL=1).  Default: the
         # bucketed exchange runs right after the replay on the communication stream.
