@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("YVB200_PRECISION", "bf16x3"), choices=["bf16x3", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="developer runs: only the timed step loops, no roofline / baselines")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -236,6 +237,14 @@ def main():
         exchange_check = float(max(((c - allc[0]).abs() / allc[0].clamp_min(1e-30)).max() for c in allc))
     t_dev, t_e2e = float(t[0]), float(t[1])
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    if a.quick:
+        print(json.dumps({"quick": True, "ms_per_step": t_dev / a.steps * 1e3, "e2e_ms_per_step": t_e2e / a.steps * 1e3,
+                          "value": pairs * world * a.steps / t_dev, "gpu_launches_per_step": step.launches_per_step,
+                          "variant": os.environ.get("YVB200_GEMM_VARIANT", "auto")}))
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

@@ -30,7 +30,8 @@ int yv_version(void);
 uint64_t yv_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
- * yv_gemm: D = epilogue(alpha * A.B^T)  on tcgen05 tensor cores (TMA-staged 128x128x64 tiles, TMEM accum)
+ * yv_gemm: D = epilogue(alpha * A.B^T)  on tcgen05 tensor cores (TMA-staged tiles, TMEM accumulators; 128x128 per CTA or
+ * 256x{128,256} per CTA pair)
  * replaces every nn.Linear / torch.matmul on the path: vilbert/vilbert.py:285-287,294,306,322,352,365,
  * 414-416,423,435,450,479,492,555-573,577,591,597,613,641,644,831,846,864,883,906,968,1358 and their
  * autograd dgrad / wgrad twins.
@@ -68,6 +69,10 @@ typedef struct {
     const uint64_t* rng;          /* device {seed, step}; NULL or drop_p == 0 disables dropout */
 } YvGemm;
 int yv_gemm(const YvGemm* g, yv_stream_t stream);
+/* Tuning / test knob (process-wide, not thread-safe): which kernel yv_gemm launches.  0 = automatic (default),
+ * 32 / 64 = one CTA per 128x128 tile (half-SM ring / persistent), 2 = CTA pairs (tcgen05 cta_group::2, 256-row
+ * pair tiles, width chosen per problem), 128 / 256 = CTA pairs with that tile width. */
+int yv_gemm_set_variant(int variant);
 
 /* fp32 -> bf16 plane pair (activations entering the path, e.g. the 2048-d region features) */
 int yv_split_planes(const float* src, int64_t ld_src, void* planes, int64_t ld_dst, int64_t plane_stride,

@@ -61,6 +61,68 @@ def test_gemm_bf16x3_layouts(L, a_mn, b_mn, shape):
     assert _rel(out, ref) < 3e-5
 
 
+@pytest.fixture
+def variant(request, L):
+    """Force one yv_gemm kernel variant for the test, restore automatic selection afterwards."""
+    L.set_gemm_variant(request.param)
+    yield request.param
+    L.set_gemm_variant(0)
+
+
+VARIANTS = [32, 64, 128, 256]
+
+
+@pytest.mark.parametrize("variant", VARIANTS, indirect=True)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(512, 384, 160), (2304, 1024, 96), (640, 1601, 104), (1024, 768, 2304), (264, 72, 40),
+                                   (768, 30522, 64)])
+def test_gemm_every_variant_matches_fp64(L, variant, a_mn, b_mn, shape):
+    """Each kernel variant (single CTA k32 / k64, CTA pairs of width 128 / 256) on whole, ragged, split-K and
+    wide problems in all four operand layouts: 3e-5 of the fp64 product."""
+    M, N, K = shape
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("transposed operand needs ld % 8 == 0 for the test helper")
+    A, B = _mk(M, K, 21), _mk(N, K, 22, 0.05)
+    out, _, _ = _run_gemm(L, A, B, a_mn, b_mn, 3)
+    ref = A.double() @ B.double().t()
+    assert not torch.isnan(out).any()
+    assert _rel(out, ref) < 3e-5
+
+
+@pytest.mark.parametrize("variant", [128, 256], indirect=True)
+def test_gemm_pair_variants_full_epilogue_bitwise_equal_single_cta(L, variant):
+    """The CTA-pair kernels run the same epilogue on the same fp32 accumulators: bias, GELU, saved pre-activation,
+    dropout, residual and plane outputs must agree with the single-CTA kernel to the last bit (same k order)."""
+    M, N, K = 640, 1048, 328
+    A, B = _mk(M, K, 31), _mk(N, K, 32, 0.1)
+    bias = _mk(1, N, 33)[0].contiguous()
+    res = _mk(M, N, 34)
+    rng = torch.tensor([99, 3], dtype=torch.int64, device="cuda")
+
+    def run():
+        aux = torch.zeros(M, N, device="cuda")
+        pl = L.Planes.empty(M, N, "cuda")
+        pl.keep.zero_()
+        out, _, _ = _run_gemm(L, A, B, False, False, 3, bias=bias, act=L.ACT_GELU, aux_out=aux, residual=res,
+                              out_planes=pl.ptr(), ld_pl=pl.ld, pl_plane_stride=pl.plane_stride, alpha=0.5,
+                              drop_p=0.1, drop_site=5, rng=rng)
+        return out, aux, pl.keep.clone()
+
+    got = run()
+    L.set_gemm_variant(32)
+    want = run()
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+
+
+@pytest.mark.parametrize("variant", [128, 256], indirect=True)
+def test_gemm_pair_variants_plain_bf16(L, variant):
+    A, B = _mk(520, 512, 3), _mk(264, 512, 4)
+    out, _, _ = _run_gemm(L, A, B, False, False, 1)
+    ref = A.bfloat16().double() @ B.bfloat16().double().t()
+    assert _rel(out, ref) < 1e-5
+
+
 def test_gemm_plain_bf16_matches_rounded_operands(L):
     A, B = _mk(384, 512, 3), _mk(256, 512, 4)
     out, _, _ = _run_gemm(L, A, B, False, False, 1)

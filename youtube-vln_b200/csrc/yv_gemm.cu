@@ -11,15 +11,7 @@
 // Operands may be K-major or MN-major (transposed views): dgrad / wgrad / attention products need no
 // explicit transposes.  Out-of-bounds rows/cols/k are zero-filled by TMA (each batch dim is its own
 // tensor-map dim), so ragged shapes (T=80, vocab 30522, 1601 classes) need no padding copies.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "../../include/yvb200.h"
-#include "yv_common.cuh"
+#include "yv_gemm_common.cuh"
 
 namespace {
 
@@ -59,125 +51,6 @@ struct Cfg {
     static_assert(PERSISTENT || STAGES * STAGE_BYTES >= NUM_EPI_WARPS * 4096, "k32 staging must fit in the ring");
 };
 
-struct KParams {
-    int M, N, K;
-    int nb0;
-    int splits, kb_per_split;   // split-K (only for un-batched launches with a linear, f32-only epilogue)
-    int total_tiles;            // tiles_m * tiles_n * batch * splits, walked persistently
-    int a_mn, b_mn;
-    float alpha;
-    int act;
-    const float* bias;
-    float* aux_out;
-    const float* aux_in;
-    const float* residual;
-    float* out32;
-    long long ld_out, out_sb0, out_sb1;
-    __nv_bfloat16* out_planes;
-    long long ld_pl, pl_sb0, pl_sb1, pl_plane_stride;
-    float drop_p;
-    unsigned drop_site;
-    const unsigned long long* rng;
-};
-
-// ------------------------------------------------------------------------------------------- PTX
-YV_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-YV_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-YV_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-YV_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a protocol bug must not hang the GPU
-    }
-}
-YV_DEVINL void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
-                           int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
-        "%7}], [%2];" ::"r"(dst),
-        "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-YV_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-YV_DEVINL void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-YV_DEVINL void tmem_ld32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
-        "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor (sm_100 "version 1")
-//   K-major  (64B swizzle) : rows of 64 B, 8-row groups 512 B apart (SBO); LBO unused
-//   MN-major (128B swizzle): 64-element chunks along M/N are LBO bytes apart, 8-k-row groups 1024 B apart (SBO)
-YV_DEVINL uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
-    d |= (uint64_t)layout << 61;   // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-    return d;
-}
-
-// one output element through the whole epilogue (ragged tile edges and unaligned leading dimensions only)
-__device__ __noinline__ void epilogue_scalar(const KParams& p, const YvDrop& drop, float acc, int n, int z, int row,
-                                             long long obase, long long pbase) {
-    if (n >= p.N) return;
-    float x = p.alpha * acc;
-    if (p.bias) x += __ldg(p.bias + n);
-    if (p.aux_out) p.aux_out[obase + n] = x;
-    if (p.act == YV_ACT_GELU) x = yv_gelu(x);
-    else if (p.act == YV_ACT_RELU) x = fmaxf(x, 0.f);
-    if (drop.thresh) x *= yv_drop_mul(drop, (uint32_t)(((long long)z * p.M + row) * p.N + n));
-    if (p.act == YV_ACT_MUL_GELU_GRAD) x *= yv_gelu_grad(p.aux_in[obase + n]);
-    else if (p.act == YV_ACT_MUL_RELU_MASK) x = p.aux_in[obase + n] > 0.f ? x : 0.f;
-    if (p.residual) x += p.residual[obase + n];
-    if (p.out32) p.out32[obase + n] = x;
-    if (p.out_planes) {
-        __nv_bfloat16 h, l;
-        yv_split(x, h, l);
-        p.out_planes[pbase + n] = h;
-        p.out_planes[pbase + n + p.pl_plane_stride] = l;
-    }
-}
-
-#ifdef YV_GEMM_TIMING
-__device__ long long yv_dbg[32];
-#define YV_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) yv_dbg[i] = clock64(); } while (0)
-#else
-#define YV_T(i)
-#endif
 
 // ------------------------------------------------------------------------------------------- kernel
 // Persistent: one CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  Two TMEM accumulators
@@ -185,7 +58,7 @@ __device__ long long yv_dbg[32];
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, PERSISTENT ? 1 : 2)
 yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const KParams p) {
+               const __grid_constant__ KParams p) {
     using C = Cfg<PASSES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -359,7 +232,6 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             ((p.pl_plane_stride & 3) == 0) &&
                             (((uintptr_t)p.out32 | (uintptr_t)p.aux_out | (uintptr_t)p.aux_in | (uintptr_t)p.residual |
                               (uintptr_t)p.bias) & 15) == 0 && (((uintptr_t)p.out_planes) & 7) == 0;
-        const int cg = lane & 7;                             // float4 column group of this lane inside a chunk
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -378,91 +250,8 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (nc >= p.N) break;                            // warp-uniform
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), raw);
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(raw[4 * g]), "r"(raw[4 * g + 1]),
-                                 "r"(raw[4 * g + 2]), "r"(raw[4 * g + 3])
-                                 : "memory");
-                }
-                __syncwarp();
-                const int n = nc + 4 * cg;
-                const bool quad_ok = vec_ok && (n + 3 < p.N);
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && quad_ok && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-#pragma unroll 2
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (lane >> 3) + 4 * i;
-                    const int row = m0 + q * 32 + r;
-                    float4 v;
-                    {
-                        const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((cg ^ (r & 7)) * 16);
-                        uint32_t x0, x1, x2, x3;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
-                        v = make_float4(__uint_as_float(x0), __uint_as_float(x1), __uint_as_float(x2), __uint_as_float(x3));
-                    }
-                    if (row >= p.M || n >= p.N) continue;
-                    const long long ob = obatch + (long long)row * p.ld_out + n;
-                    const long long pb = pbatch + (long long)row * p.ld_pl + n;
-                    if (!quad_ok) {                              // ragged edge / unaligned leading dimension
-                        epilogue_scalar(p, drop, v.x, n, z, row, ob - n, pb - n);
-                        epilogue_scalar(p, drop, v.y, n + 1, z, row, ob - n, pb - n);
-                        epilogue_scalar(p, drop, v.z, n + 2, z, row, ob - n, pb - n);
-                        epilogue_scalar(p, drop, v.w, n + 3, z, row, ob - n, pb - n);
-                        continue;
-                    }
-                    v.x = p.alpha * v.x + bias4.x; v.y = p.alpha * v.y + bias4.y;
-                    v.z = p.alpha * v.z + bias4.z; v.w = p.alpha * v.w + bias4.w;
-                    if (p.splits > 1) {
-                        // split-K: partial sums meet in a zero-initialised f32 output through vector reductions; the
-                        // epilogue is linear here (bias and residual come from split 0, dropout scales every partial)
-                        if (drop.thresh) {
-                            const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
-                            v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
-                            v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
-                        }
-                        if (p.residual && split == 0) {
-                            const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
-                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                        }
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out32 + ob), "f"(v.x), "f"(v.y),
-                                     "f"(v.z), "f"(v.w)
-                                     : "memory");
-                        continue;
-                    }
-                    if (p.aux_out) *reinterpret_cast<float4*>(p.aux_out + ob) = v;
-                    if (p.act == YV_ACT_GELU) {
-                        v.x = yv_gelu(v.x); v.y = yv_gelu(v.y); v.z = yv_gelu(v.z); v.w = yv_gelu(v.w);
-                    } else if (p.act == YV_ACT_RELU) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
-                    if (drop.thresh) {
-                        const uint32_t i0 = (uint32_t)(((long long)z * p.M + row) * p.N + n);
-                        v.x *= yv_drop_mul(drop, i0); v.y *= yv_drop_mul(drop, i0 + 1);
-                        v.z *= yv_drop_mul(drop, i0 + 2); v.w *= yv_drop_mul(drop, i0 + 3);
-                    }
-                    if (p.act == YV_ACT_MUL_GELU_GRAD) {
-                        const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
-                        v.x *= yv_gelu_grad(t.x); v.y *= yv_gelu_grad(t.y); v.z *= yv_gelu_grad(t.z); v.w *= yv_gelu_grad(t.w);
-                    } else if (p.act == YV_ACT_MUL_RELU_MASK) {
-                        const float4 t = *reinterpret_cast<const float4*>(p.aux_in + ob);
-                        v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f;
-                        v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-                    }
-                    if (p.residual) {
-                        const float4 t = *reinterpret_cast<const float4*>(p.residual + ob);
-                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                    }
-                    if (p.out32) *reinterpret_cast<float4*>(p.out32 + ob) = v;
-                    if (p.out_planes) {
-                        __align__(8) __nv_bfloat16 h4[4], l4[4];
-                        yv_split(v.x, h4[0], l4[0]); yv_split(v.y, h4[1], l4[1]);
-                        yv_split(v.z, h4[2], l4[2]); yv_split(v.w, h4[3], l4[3]);
-                        *reinterpret_cast<uint2*>(p.out_planes + pb) = *reinterpret_cast<uint2*>(h4);
-                        *reinterpret_cast<uint2*>(p.out_planes + pb + p.pl_plane_stride) = *reinterpret_cast<uint2*>(l4);
-                    }
-                }
-                __syncwarp();                                    // staging buffer is reused by the next chunk
+                YV_T64(8);
+                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok);
             }
             // this warp has finished reading its TMEM lanes of accumulator `acc`: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -485,51 +274,7 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
-// ------------------------------------------------------------------------------------------- host
-PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
-
-int get_encode() {
-    if (g_encode) return 0;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-        yv_set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
-        return 1;
-    }
-    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-    return 0;
-}
-
-int make_map(CUtensorMap* map, const YvOperand& o, int passes, const char* which) {
-    YV_CHECK(o.ptr != nullptr, "yv_gemm: operand %s is NULL", which);
-    YV_CHECK(((uintptr_t)o.ptr & 15) == 0, "yv_gemm: operand %s not 16-byte aligned", which);
-    YV_CHECK(o.inner > 0 && o.rows > 0 && o.nb0 > 0 && o.nb1 > 0, "yv_gemm: operand %s has empty extent", which);
-    YV_CHECK((o.ld & 7) == 0 && o.ld >= o.inner, "yv_gemm: operand %s ld=%lld must be a multiple of 8 and >= inner=%lld",
-             which, (long long)o.ld, (long long)o.inner);
-    YV_CHECK((o.nb0 == 1 || (o.sb0 & 7) == 0) && (o.nb1 == 1 || (o.sb1 & 7) == 0),
-             "yv_gemm: operand %s batch strides must be multiples of 8 elements", which);
-    YV_CHECK(passes == 1 || ((o.plane_stride & 7) == 0 && o.plane_stride > 0),
-             "yv_gemm: operand %s plane_stride must be a positive multiple of 8", which);
-    const int nplanes = passes == 3 ? 2 : 1;
-    cuuint64_t dims[5] = {(cuuint64_t)o.inner, (cuuint64_t)o.rows, (cuuint64_t)o.nb0, (cuuint64_t)o.nb1,
-                          (cuuint64_t)nplanes};
-    // strides of dims 1..4 in bytes (dim 0 is contiguous); unused dims get a harmless valid stride
-    const cuuint64_t row_b = (cuuint64_t)o.ld * 2;
-    cuuint64_t strides[4] = {row_b, o.nb0 > 1 ? (cuuint64_t)o.sb0 * 2 : row_b, o.nb1 > 1 ? (cuuint64_t)o.sb1 * 2 : row_b,
-                             nplanes > 1 ? (cuuint64_t)o.plane_stride * 2 : row_b};
-    // K-major: 32 k-elements (64 B, 64B swizzle) x 128 rows; MN-major: 64 m/n-elements (128 B, 128B swizzle) x 32 k-rows
-    cuuint32_t box[5] = {(cuuint32_t)(o.mn_major ? 64 : BLOCK_K), (cuuint32_t)(o.mn_major ? BLOCK_K : BLOCK_M), 1, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(o.ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, (o.mn_major || BLOCK_K == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    YV_CHECK(r == CUDA_SUCCESS, "yv_gemm: cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", which,
-             (int)r, (long long)o.inner, (long long)o.rows, (long long)o.ld);
-    return 0;
-}
 
 }  // namespace
 
@@ -551,12 +296,13 @@ extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
              b.mn_major, g->N, g->K);
     YV_CHECK(a.nb0 == b.nb0 && a.nb1 == b.nb1, "yv_gemm: batch counts differ");
     CUtensorMap ma, mb;
-    if (make_map(&ma, a, g->passes, "A")) return 1;
-    if (make_map(&mb, b, g->passes, "B")) return 1;
+    if (make_map(&ma, a, g->passes, "A", BLOCK_K, BLOCK_M)) return 1;
+    if (make_map(&mb, b, g->passes, "B", BLOCK_K, BLOCK_N)) return 1;
 
     KParams p;
     p.M = g->M; p.N = g->N; p.K = g->K;
     p.nb0 = (int)a.nb0;
+    p.pair_n = 0; p.stages = 0;
     p.a_mn = a.mn_major ? 1 : 0;
     p.b_mn = b.mn_major ? 1 : 0;
     p.alpha = g->alpha;

@@ -1,0 +1,356 @@
+// yv_gemm_pair: the CTA-pair (tcgen05 cta_group::2) variant of yv_gemm.  sm_100a only.
+//
+// Why: with one CTA per 128x128 tile every SM pulls a full A tile and a full B tile (hi and lo planes) through the
+// L2 -> SM crossbar for 3 x 128x128x32 MMAs; ncu shows the 2304x3072x1024 projection moving 453 MB at ~5500 B/clk
+// (the chip-wide L2 -> SM limit) with the tensor pipe 53 % busy.  Here two CTAs on the two SMs of a TPC share one
+// 256 x PAIR_N tile: each CTA stages its own 128 rows of A and only HALF of the B tile, and the leader's
+// tcgen05.mma.cta_group::2 (UMMA_M = 256) reads both halves from both shared memories.  PAIR_N = 128 keeps the CTA
+// count of the 128x128 tiling with 25 % fewer operand bytes per FLOP, PAIR_N = 256 halves the bytes per FLOP.
+//
+// One cluster of 2 CTAs per pair tile, 320 threads per CTA:
+//   warp 0   : TMA producer (one lane, both CTAs) -- own A rows + own half of B into a 3- or 6-stage ring of 32 KB
+//              stages; every load signals the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1   : TMEM allocation (cta_group::2, both CTAs); the leader's lane 0 issues every MMA and commits with
+//              multicast arrives to the empty / accumulator-full barriers of both CTAs
+//   warps 2-9: epilogue of this CTA's 128 rows x PAIR_N columns (same fused epilogue as yv_gemm.cu)
+#include "yv_gemm_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;                                  // rows per CTA; the pair tile covers 256
+constexpr int BLOCK_K = 32;                                   // 64 B rows, 64B swizzle for K-major tiles
+constexpr int UMMA_K = 16;
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 8 KB: one plane of 128 rows x 32 k
+constexpr int NUM_THREADS = 320;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int MAX_STAGES = 6;
+constexpr int KMAJ_SBO = BLOCK_K * 2 * 8;
+
+template <int PASSES>
+struct PCfg {
+    static constexpr int PLANES = PASSES == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * 2 * TILE_BYTES;   // A_hi, B_hi, (A_lo, B_lo); B slots hold <= 128 rows
+    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
+};
+
+YV_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+YV_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) inside the CTA of rank `rank`
+YV_DEVINL uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
+YV_DEVINL void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6, %7}], [%2];" ::"r"(dst),
+        "l"((unsigned long long)map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+YV_DEVINL void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+YV_DEVINL void umma2_commit(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((unsigned short)3)
+        : "memory");
+}
+
+template <int PASSES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 2)
+yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ KParams p) {
+    using C = PCfg<PASSES>;
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs: the MMA descriptors and the multicast commits address the peer by offset
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * C::STAGE_BYTES);
+    // bars: [0,6) full (used in the leader only), [6,12) empty, 12 accumulator full; then the TMEM base address word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair_n = p.pair_n;
+    const int nb_half = pair_n >> 1;                             // B rows staged by each CTA
+    const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int tiles_n = (p.N + pair_n - 1) / pair_n;
+    const int tiles_mp = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    if (threadIdx.x == 0) YV_T(0);
+    yv_pdl_trigger();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_b) : "memory");
+    }
+    if (warp == 1) {     // the same warp of both CTAs allocates the pair's accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)pair_n)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();      // barriers of both CTAs are initialised before any remote arrive / complete_tx
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    yv_pdl_wait();
+    if (threadIdx.x == 0) YV_T(1);
+
+    // pair tile -> (split, n block, m pair, batch); m varies fastest so concurrently running pairs share B in L2
+    int t = (int)(blockIdx.x >> 1);
+    const int split = t % p.splits;
+    t /= p.splits;
+    const int m0 = (t % tiles_mp) * (2 * BLOCK_M) + (int)rank * BLOCK_M;   // first row of THIS CTA
+    t /= tiles_mp;
+    const int n0 = (t % tiles_n) * pair_n;
+    const int z = t / tiles_n;
+    const int b0 = z % p.nb0, b1 = z / p.nb0;
+    const int kb_lo = split * p.kb_per_split;
+    const int num_kb = min(p.kb_per_split, total_kb - kb_lo);
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) ==========================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(C::PLANES * (TILE_BYTES + nb_half * BLOCK_K * 2));
+            const int nb0_row = n0 + (int)rank * nb_half;                  // first B row staged by this CTA
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t lbar = mapa_rank(full_bar(stage), 0);       // the leader's barrier collects both CTAs' bytes
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * tx_bytes);
+                const int k0 = (kb_lo + kb) * BLOCK_K;
+#pragma unroll
+                for (int pl = 0; pl < C::PLANES; ++pl) {
+                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                    if (!p.a_mn) {
+                        tma_load_5d_pair(sa, &map_a, lbar, k0, m0, b0, b1, pl);
+                    } else {
+                        tma_load_5d_pair(sa, &map_a, lbar, m0, k0, b0, b1, pl);
+                        tma_load_5d_pair(sa + TILE_BYTES / 2, &map_a, lbar, m0 + 64, k0, b0, b1, pl);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_5d_pair(sb, &map_b, lbar, k0, nb0_row, b0, b1, pl);
+                    } else {
+                        tma_load_5d_pair(sb, &map_b, lbar, nb0_row, k0, b0, b1, pl);
+                        if (nb_half > 64) tma_load_5d_pair(sb + TILE_BYTES / 2, &map_b, lbar, nb0_row + 64, k0, b0, b1, pl);
+                    }
+                }
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) ======================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
+                                   ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                                   ((uint32_t)(pair_n >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+            const uint32_t a_step = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            const uint32_t b_step = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t accum = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                if (kb == 0) YV_T(2);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                uint64_t da[2], db[2];
+#pragma unroll
+                for (int pl = 0; pl < C::PLANES; ++pl) {
+                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
+                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, 4);
+                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, 4);
+                }
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    if (PASSES == 3) {
+                        umma2_bf16(tmem_base, da[1] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                        accum = 1;
+                        umma2_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[1] + (uint64_t)(b_step * k), idesc, 1);
+                    }
+                    umma2_bf16(tmem_base, da[0] + (uint64_t)(a_step * k), db[0] + (uint64_t)(b_step * k), idesc, accum);
+                    accum = 1;
+                }
+                umma2_commit(empty_bar(stage));      // frees this ring slot in both CTAs once the MMAs retire
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            YV_T(3);
+            umma2_commit(tmem_full_bar);             // accumulators of both CTAs complete -> both epilogues
+        }
+    } else {
+        // ===================================== epilogue (both CTAs, own 128 rows) ================
+        const int ew = warp - 2;
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int half = ew >> 2;
+        const int cpw = pair_n >> 6;                         // 32-column chunks per warp: 2 (PAIR_N 128) or 4 (256)
+        const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
+        const uint32_t stg = smem_base + (uint32_t)ew * 4096u;   // staging reuses the drained operand ring
+        const bool vec_ok = ((p.ld_out & 3) == 0) && ((p.out_sb0 & 3) == 0) && ((p.out_sb1 & 3) == 0) &&
+                            ((p.ld_pl & 3) == 0) && ((p.pl_sb0 & 3) == 0) && ((p.pl_sb1 & 3) == 0) &&
+                            ((p.pl_plane_stride & 3) == 0) &&
+                            (((uintptr_t)p.out32 | (uintptr_t)p.aux_out | (uintptr_t)p.aux_in | (uintptr_t)p.residual |
+                              (uintptr_t)p.bias) & 15) == 0 && (((uintptr_t)p.out_planes) & 7) == 0;
+        const long long obatch = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1;
+        const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
+        mbar_wait(tmem_full_bar, 0);
+        if (threadIdx.x == 64) YV_T(4);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (m0 + q * 32 < p.M) {                             // warp-uniform: rows of this lane quarter exist
+#pragma unroll 1
+            for (int cc = 0; cc < cpw; ++cc) {
+                const int c = half * cpw + cc;
+                const int nc = n0 + c * 32;
+                if (nc >= p.N) break;                        // warp-uniform
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
+                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok);
+            }
+        }
+    }
+
+    if (threadIdx.x == 64) YV_T(5);
+    // both CTAs: nobody may leave (or free TMEM) while the peer's tensor core can still read this CTA's operands
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (threadIdx.x == 0) YV_T(6);
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)pair_n)
+                     : "memory");
+    }
+}
+
+const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
+
+}  // namespace
+
+void yv_count_launch();
+
+// pair_n: 128 or 256 (0 = choose).  Un-batched and batched problems alike; M is tiled in 256-row pair tiles.
+extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
+    YV_CHECK(g != nullptr, "yv_gemm: NULL args");
+    YV_CHECK(g->passes == 1 || g->passes == 3, "yv_gemm: passes must be 1 or 3 (got %d)", g->passes);
+    YV_CHECK(g->M > 0 && g->N > 0 && g->K > 0, "yv_gemm: empty problem M=%d N=%d K=%d", g->M, g->N, g->K);
+    YV_CHECK(g->out32 || g->out_planes, "yv_gemm: no output requested");
+    YV_CHECK(pair_n == 0 || pair_n == 128 || pair_n == 256, "yv_gemm_pair: pair_n must be 0, 128 or 256");
+    if (get_encode()) return 1;
+    const YvOperand &a = g->a, &b = g->b;
+    YV_CHECK((a.mn_major ? a.inner : a.rows) == g->M && (a.mn_major ? a.rows : a.inner) == g->K,
+             "yv_gemm: A extents (%lld x %lld, mn_major=%d) do not match M=%d K=%d", (long long)a.rows, (long long)a.inner,
+             a.mn_major, g->M, g->K);
+    YV_CHECK((b.mn_major ? b.inner : b.rows) == g->N && (b.mn_major ? b.rows : b.inner) == g->K,
+             "yv_gemm: B extents (%lld x %lld, mn_major=%d) do not match N=%d K=%d", (long long)b.rows, (long long)b.inner,
+             b.mn_major, g->N, g->K);
+    YV_CHECK(a.nb0 == b.nb0 && a.nb1 == b.nb1, "yv_gemm: batch counts differ");
+    const long long batch = a.nb0 * a.nb1;
+    const int tiles_mp = (g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    if (pair_n == 0) {
+        // 256-wide pair tiles halve the operand bytes per FLOP but also halve the CTA count: take them only when
+        // the 128-wide tiling would need more than one resident wave (2 CTAs per SM)
+        const long long ctas128 = 2LL * tiles_mp * ((g->N + 127) / 128) * batch;
+        pair_n = ctas128 > 2 * 148 ? 256 : 128;
+    }
+    CUtensorMap ma, mb;
+    if (make_map(&ma, a, g->passes, "A", BLOCK_K, BLOCK_M)) return 1;
+    if (make_map(&mb, b, g->passes, "B", BLOCK_K, pair_n / 2)) return 1;
+
+    KParams p;
+    p.M = g->M; p.N = g->N; p.K = g->K;
+    p.nb0 = (int)a.nb0;
+    p.a_mn = a.mn_major ? 1 : 0;
+    p.b_mn = b.mn_major ? 1 : 0;
+    p.alpha = g->alpha;
+    p.act = g->act;
+    p.bias = g->bias;
+    p.aux_out = g->aux_out;
+    p.aux_in = g->aux_in;
+    p.residual = g->residual;
+    p.out32 = g->out32;
+    p.ld_out = g->ld_out; p.out_sb0 = g->out_sb0; p.out_sb1 = g->out_sb1;
+    p.out_planes = reinterpret_cast<__nv_bfloat16*>(g->out_planes);
+    p.ld_pl = g->ld_pl; p.pl_sb0 = g->pl_sb0; p.pl_sb1 = g->pl_sb1; p.pl_plane_stride = g->pl_plane_stride;
+    p.drop_p = g->drop_p; p.drop_site = g->drop_site;
+    p.rng = reinterpret_cast<const unsigned long long*>(g->rng);
+    p.pair_n = pair_n;
+    YV_CHECK((g->act != YV_ACT_MUL_GELU_GRAD && g->act != YV_ACT_MUL_RELU_MASK) || g->aux_in,
+             "yv_gemm: act %d needs aux_in", g->act);
+
+    const int pairs = tiles_mp * ((g->N + pair_n - 1) / pair_n);
+    const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
+    p.splits = 1;
+    p.kb_per_split = total_kb;
+    // split-K as in yv_gemm.cu: few tiles, linear epilogue into a plain f32 output (zero-filled by a memset node)
+    const bool linear_epi = g->act == YV_ACT_NONE && !g->aux_out && !g->out_planes && g->out32 &&
+                            (g->ld_out % 4 == 0) && (g->N % 4 == 0) && (((uintptr_t)g->out32) & 15) == 0 &&
+                            (!g->residual || g->residual != g->out32) && (!g->bias || (((uintptr_t)g->bias) & 15) == 0) &&
+                            (!g->residual || (((uintptr_t)g->residual) & 15) == 0);
+    if (batch == 1 && linear_epi && pairs * 4 <= 148 && total_kb >= 8 && g_split_k) {
+        int s = 148 / (2 * pairs);
+        if (s > total_kb / 4) s = total_kb / 4;
+        if (s > 16) s = 16;
+        if (s >= 2) {
+            p.kb_per_split = (total_kb + s - 1) / s;
+            p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+        }
+    }
+    const long long total_pairs = (long long)pairs * batch * p.splits;
+    YV_CHECK(2 * total_pairs < 2147483647LL, "yv_gemm: too many tiles");
+    p.total_tiles = (int)total_pairs;
+    // one resident CTA per SM can afford the deep ring (more bytes in flight per SM); beyond that two CTAs share an SM
+    p.stages = 2 * total_pairs <= 148 ? MAX_STAGES : 3;
+    dim3 grid((unsigned)(2 * total_pairs), 1, 1);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p.splits > 1)
+        YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PCfg<1>::smem_bytes(MAX_STAGES)));
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PCfg<3>::smem_bytes(MAX_STAGES)));
+        attr_set = true;
+    }
+    if (g->passes == 3)
+        YV_CUDA(yv_launch(yv_gemm_pair_kernel<3>, grid, dim3(NUM_THREADS), PCfg<3>::smem_bytes(p.stages), st, ma, mb, p));
+    else
+        YV_CUDA(yv_launch(yv_gemm_pair_kernel<1>, grid, dim3(NUM_THREADS), PCfg<1>::smem_bytes(p.stages), st, ma, mb, p));
+    YV_CUDA(cudaGetLastError());
+    yv_count_launch();
+    return 0;
+}

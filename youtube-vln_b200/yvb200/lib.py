@@ -19,7 +19,7 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_MUL_GELU_GRAD, ACT_MUL_RELU_MASK = 0, 1, 2, 3,
 
 #: every symbol include/yvb200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_split_planes", "yv_split_multi",
+    "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_set_variant", "yv_split_planes", "yv_split_multi",
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
@@ -79,6 +79,11 @@ def available() -> bool:
 
 def launch_count() -> int:
     return int(load().yv_launch_count())
+
+
+def set_gemm_variant(variant: int = 0):
+    """Tuning / test knob: 0 automatic, 32 / 64 single-CTA kernels, 2 CTA pairs, 128 / 256 CTA pairs of that width."""
+    _check(load().yv_gemm_set_variant(C.c_int(variant)), "gemm_set_variant")
 
 
 def _check(rc: int, what: str):
