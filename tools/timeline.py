@@ -39,7 +39,9 @@ busy += cur_e - cur_s
 print(f"GPU busy (union) {busy/1e3:.3f} ms, idle gaps {(t1 - t0 - busy)/1e3:.3f} ms")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in ks:
-    n = e["name"].split("(")[0][-60:]
+    import re
+    m = re.search(r"(yv_gemm_pair_kernel<\d>|yv_gemm_kernel<\d>|[a-z_0-9]+_kernel(<\d+>)?)", e["name"])
+    n = m.group(1) if m else e["name"][:60]
     agg[n][0] += 1; agg[n][1] += e["dur"]
 for n, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
     print(f"{d/1e3:8.3f} ms {c:5d}x {d/c:7.1f} us  {n}")
@@ -52,3 +54,23 @@ lvl, last, hist = 0, pts[0][0], collections.Counter()
 for t, d in pts:
     hist[lvl] += t - last; last = t; lvl += d
 print("time by #kernels in flight:", {k: round(v/1e3, 3) for k, v in sorted(hist.items())})
+
+# per-kernel-family: time during which it is the ONLY kernel running (serial exposure)
+ivs = sorted((e["ts"], e["ts"] + e["dur"], e["name"]) for e in ks)
+import re, heapq
+events = []
+for s0, f0, nm in ivs:
+    events.append((s0, 1, nm)); events.append((f0, -1, nm))
+events.sort(key=lambda x: (x[0], x[1]))
+active = collections.Counter(); last = events[0][0]; alone = collections.Counter()
+def fam(nm):
+    m = re.search(r"(yv_gemm_pair_kernel|yv_gemm_kernel|[a-z_0-9]+_kernel)", nm)
+    return m.group(1) if m else nm[:40]
+for t, d, nm in events:
+    tot_active = sum(active.values())
+    if tot_active == 1:
+        only = [k for k, v in active.items() if v > 0][0]
+        alone[only] += t - last
+    last = t
+    active[fam(nm)] += d
+print("time running alone (ms):", {k: round(v / 1e3, 3) for k, v in alone.most_common(12)})

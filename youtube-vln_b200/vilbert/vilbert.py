@@ -258,8 +258,25 @@ class BertSelfOutput(_DenseResidualNorm):
         super().__init__(config.hidden_size, config.hidden_size, config.hidden_dropout_prob)
 
 
+def _fused_ffn(intermediate, output, x):
+    """output(intermediate(x), x); on CUDA with a GELU intermediate the pair runs as one fused autograd node."""
+    if x.is_cuda and intermediate._act_name == "gelu" and os.environ.get("YVB200_FUSED_BLOCKS", "1") != "0":
+        p = output.dropout.p if output.training else 0.0
+        return _cuda_ops(x).ffn(x, intermediate.dense.weight, intermediate.dense.bias, output.dense.weight,
+                                output.dense.bias, output.LayerNorm.weight, output.LayerNorm.bias, p, output._site)
+    return output(intermediate(x), x)
+
+
 class _Attention(nn.Module):
     def forward(self, input_tensor, attention_mask):
+        if input_tensor.is_cuda and os.environ.get("YVB200_FUSED_BLOCKS", "1") != "0":
+            # self-attention + output projection + residual + LayerNorm as one fused autograd node
+            sa, so = self.self, self.output
+            return _cuda_ops(input_tensor).attention_block(
+                input_tensor, attention_mask, sa.query.weight, sa.query.bias, sa.key.weight, sa.key.bias,
+                sa.value.weight, sa.value.bias, so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+                sa.num_attention_heads, sa.dropout.p if sa.training else 0.0, sa._site,
+                so.dropout.p if so.training else 0.0, so._site)
         ctx, probs = self.self(input_tensor, attention_mask)
         return self.output(ctx, input_tensor), probs
 
@@ -284,7 +301,7 @@ class BertOutput(_DenseResidualNorm):
 class _TransformerBlock(nn.Module):
     def forward(self, hidden_states, attention_mask):
         a, probs = self.attention(hidden_states, attention_mask)
-        return self.output(self.intermediate(a), a), probs
+        return _fused_ffn(self.intermediate, self.output, a), probs
 
 
 class BertLayer(_TransformerBlock):
@@ -452,16 +469,16 @@ class BertConnectionLayer(nn.Module):
             with torch.cuda.stream(side):
                 a1 = ops.dense_res_ln(ctx_v, input_tensor1, bo.dense1.weight, bo.dense1.bias, bo.LayerNorm1.weight,
                                       bo.LayerNorm1.bias, bo.dropout1.p if self.training else 0.0, bo._site1)
-                o1 = self.v_output(self.v_intermediate(a1), a1)
+                o1 = _fused_ffn(self.v_intermediate, self.v_output, a1)
             a2 = ops.dense_res_ln(ctx_t, input_tensor2, bo.dense2.weight, bo.dense2.bias, bo.LayerNorm2.weight,
                                   bo.LayerNorm2.bias, bo.dropout2.p if self.training else 0.0, bo._site2)
-            o2 = self.t_output(self.t_intermediate(a2), a2)
+            o2 = _fused_ffn(self.t_intermediate, self.t_output, a2)
             cur.wait_stream(side)
             _share(o1, cur)
             return o1, o2, probs
         a1, a2 = self.biOutput(ctx_v, input_tensor1, ctx_t, input_tensor2)
-        o1 = self.v_output(self.v_intermediate(a1), a1)
-        o2 = self.t_output(self.t_intermediate(a2), a2)
+        o1 = _fused_ffn(self.v_intermediate, self.v_output, a1)
+        o2 = _fused_ffn(self.t_intermediate, self.t_output, a2)
         return o1, o2, probs
 
 

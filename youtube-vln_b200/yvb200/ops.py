@@ -7,6 +7,8 @@ Each block mirrors one sub-module of the reference (vilbert/vilbert.py) and owns
   DenseActLN     LN(gelu(x W^T + b))                     Bert(Img)PredictionHeadTransform :863-886
   SelfAttention  QKV proj -> softmax(QK^T/sqrt(d)+m) V   Bert(Image)SelfAttention :284-311, :413-440
   BiAttention    both cross-stream directions            BertBiAttention :552-618
+  AttnBlock      attention + out-proj + residual + LN    Bert(Image)Attention :328-337, :456-464 (one node)
+  FFN            LN(dropout(W2 gelu(W1 x)) + x)          Bert(Image)Intermediate+Output (one node)
   TextEmbed      gather-sum -> LN -> dropout             BertEmbeddings :240-256
   ImageEmbed     2048->H GEMM + location terms -> LN     BertImageEmbeddings :1356-1370
 
@@ -552,6 +554,177 @@ def self_attention(x, mask, Wq, bq, Wk, bk, Wv, bv, heads: int, drop_p: float, s
     c = SelfAttentionFn.apply(x, mask, Wq, bq, Wk, bk, Wv, bv, spec)
     attach_planes(c, spec.out_planes)
     return c, spec.probs
+
+
+class AttnBlockFn(Function):
+    """Self-attention + output projection + residual + LayerNorm as ONE autograd node: the reference's
+    ``Bert(Image)Attention`` = ``Bert(Image)SelfOutput(Bert(Image)SelfAttention(x), x)`` (vilbert/vilbert.py:328-337,
+    :456-464).  Inside one node the fp32 copies of the context and of its gradient are never written, the out-proj
+    dgrad emits the bf16 planes the attention backward consumes (no split pass), and the residual gradient is added in
+    the epilogue of the QKV dgrad instead of by a separate autograd accumulation kernel."""
+
+    @staticmethod
+    def forward(ctx, x, mask, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, spec):
+        r = rt(x.device)
+        pairs, S, K = x.shape
+        H = Wq.shape[0]
+        heads = spec.heads
+        dh = H // heads
+        x2 = _c2d(x)
+        if x2.stride(0) != K:
+            x2 = x2.contiguous()
+        M = pairs * S
+        dev = x.device
+        xp = planes_of(x, x2)
+        wqkv = r.arena.get((Wq, Wk, Wv))
+        wo = r.arena.get((Wo,))
+        m2 = _mask2d(mask, pairs, S)
+        qkv = Planes.empty(M, 3 * H, dev)
+        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wqkv), passes=r.passes, bias=_cat_bias((bq, bk, bv)),
+               out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
+        cp = Planes.empty(M, H, dev)
+        q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
+        P, Pp = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None)
+        s = _f32(M, H, device=dev)
+        L.gemm(M, H, H, L.op_of(cp), L.op_of(wo), passes=r.passes, bias=bo, residual=x2, out32=s, ld_out=H,
+               drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=r.rng)
+        z = _f32(M, H, device=dev)
+        zp = Planes.empty(M, H, dev)
+        stats = _f32(M, 2, device=dev)
+        L.layernorm_fwd(s, gamma, beta, LN_EPS, z, zp, stats, M, H)
+        ctx.r, ctx.spec = r, spec
+        ctx.keep = (xp, wqkv, wo, qkv, Pp, cp)
+        ctx.dims = (pairs, S, K, H, heads, dh)
+        ctx.save_for_backward(P, s, stats, gamma)
+        spec.out_planes = zp
+        spec.probs = P
+        return z.view(pairs, S, H)
+
+    @staticmethod
+    def backward(ctx, dz):
+        r, spec = ctx.r, ctx.spec
+        pairs, S, K, H, heads, dh = ctx.dims
+        xp, wqkv, wo, qkv, Pp, cp = ctx.keep
+        P, s, stats, gamma = ctx.saved_tensors
+        M = pairs * S
+        dev = dz.device
+        ds = _f32(M, H, device=dev)
+        dsp = Planes.empty(M, H, dev)
+        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, d(out bias)
+        L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.out_drop_p,
+                        pre_drop_site=spec.out_site, rng=r.rng, dbias=acc[2])
+        dWo = _f32(H, H, device=dev)
+        dOp = Planes.empty(M, H, dev)
+        cur = torch.cuda.current_stream(dev)
+        side = r.helper() if r.concurrent else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                     # wgrad of the output projection
+            L.gemm(H, H, M, L.op_of(dsp, True), L.op_of(cp, True), passes=r.passes, out32=dWo, ld_out=H)
+        # dgrad of the output projection straight into the planes the attention backward reads
+        L.gemm(M, H, H, L.op_of(dsp), L.op_of(wo, True), passes=r.passes, out_planes=dOp.ptr(), ld_pl=dOp.ld,
+               pl_plane_stride=dOp.plane_stride)
+        dqkv = Planes.empty(M, 3 * H, dev)
+        q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
+        _attn_bwd(r, dOp, q, k, v, P, Pp, pairs, heads, dh, spec.drop_p, spec.site,
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
+        cur.wait_stream(side)
+        need_dx = ctx.needs_input_grad[0]
+        dx, dW, db = _linear_bwd(r, dqkv, xp, wqkv, M, 3 * H, K, dev, need_dx, True, dx_residual=ds)
+        if not need_dx:
+            dx = None
+        return ((dx.view(pairs, S, K) if dx is not None else None), None,
+                dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:], dWo, acc[2], acc[0], acc[1], None)
+
+
+def attention_block(x, mask, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, heads: int, drop_p: float, site: int,
+                    out_drop_p: float, out_site: int):
+    """LN(dropout(out_proj(attention(x))) + x); returns (output, attention probabilities)."""
+    spec = types.SimpleNamespace(heads=heads, drop_p=float(drop_p), site=site, out_drop_p=float(out_drop_p),
+                                 out_site=out_site, out_planes=None, probs=None)
+    z = AttnBlockFn.apply(x, mask, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, spec)
+    attach_planes(z, spec.out_planes)
+    return z, spec.probs
+
+
+class FFNFn(Function):
+    """Feed-forward block as ONE autograd node: ``LN(dropout(W2 gelu(W1 x + b1) + b2) + x)`` -- the reference's
+    ``Bert(Image)Output(Bert(Image)Intermediate(x), x)`` (vilbert/vilbert.py:340-368, :467-495, used at :380-381,
+    :507-508, :674-677).  The hidden activation only exists as bf16 planes (plus its fp32 pre-activation for GELU'),
+    the dgrad of W2 multiplies by GELU'(pre) in its epilogue and emits planes (no activation-backward pass), and the
+    residual gradient rides in the epilogue of the W1 dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, gamma, beta, spec):
+        r = rt(x.device)
+        x2 = _c2d(x)
+        M, H = x2.shape
+        if x2.stride(0) != H:
+            x2 = x2.contiguous()
+        FF = W1.shape[0]
+        dev = x.device
+        xp = planes_of(x, x2)
+        w1 = r.arena.get((W1,))
+        w2 = r.arena.get((W2,))
+        pre = _f32(M, FF, device=dev) if any(ctx.needs_input_grad) else None
+        hp = Planes.empty(M, FF, dev)
+        L.gemm(M, FF, H, L.op_of(xp), L.op_of(w1), passes=r.passes, bias=b1, act=L.ACT_GELU, aux_out=pre, ld_out=FF,
+               out_planes=hp.ptr(), ld_pl=hp.ld, pl_plane_stride=hp.plane_stride)
+        s = _f32(M, H, device=dev)
+        L.gemm(M, H, FF, L.op_of(hp), L.op_of(w2), passes=r.passes, bias=b2, residual=x2, out32=s, ld_out=H,
+               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng)
+        z = _f32(M, H, device=dev)
+        zp = Planes.empty(M, H, dev)
+        stats = _f32(M, 2, device=dev)
+        L.layernorm_fwd(s, gamma, beta, LN_EPS, z, zp, stats, M, H)
+        ctx.r, ctx.spec, ctx.dims = r, spec, (M, H, FF)
+        ctx.keep = (xp, w1, w2, hp)
+        ctx.save_for_backward(pre, s, stats, gamma)
+        ctx.xshape = x.shape
+        spec.out_planes = zp
+        return z.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dz):
+        r, spec = ctx.r, ctx.spec
+        M, H, FF = ctx.dims
+        xp, w1, w2, hp = ctx.keep
+        pre, s, stats, gamma = ctx.saved_tensors
+        dev = dz.device
+        ds = _f32(M, H, device=dev)
+        dsp = Planes.empty(M, H, dev)
+        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, db2
+        L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.drop_p,
+                        pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+        dW2 = _f32(H, FF, device=dev)
+        dW1 = _f32(FF, H, device=dev)
+        db1 = _f32(FF, device=dev)
+        dprep = Planes.empty(M, FF, dev)
+        cur = torch.cuda.current_stream(dev)
+        side = r.helper() if r.concurrent else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                     # dW2 = ds^T . h
+            L.gemm(H, FF, M, L.op_of(dsp, True), L.op_of(hp, True), passes=r.passes, out32=dW2, ld_out=FF)
+        # d(pre) = (ds . W2) * gelu'(pre), written as planes only
+        L.gemm(M, FF, H, L.op_of(dsp), L.op_of(w2, True), passes=r.passes, act=L.ACT_MUL_GELU_GRAD, aux_in=pre, ld_out=FF,
+               out_planes=dprep.ptr(), ld_pl=dprep.ld, pl_plane_stride=dprep.plane_stride)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                     # dW1 = d(pre)^T . x ; db1 = colsum(d(pre))
+            L.gemm(FF, H, M, L.op_of(dprep, True), L.op_of(xp, True), passes=r.passes, out32=dW1, ld_out=H)
+            L.colsum_planes(dprep, db1)
+        dx = None
+        if ctx.needs_input_grad[0]:                                       # dx = d(pre) . W1 + ds (residual branch)
+            dx = _f32(M, H, device=dev)
+            L.gemm(M, H, FF, L.op_of(dprep), L.op_of(w1, True), passes=r.passes, out32=dx, ld_out=H, residual=ds)
+        cur.wait_stream(side)
+        return ((dx.view(ctx.xshape) if dx is not None else None), dW1, db1, dW2, acc[2], acc[0], acc[1], None)
+
+
+def ffn(x, W1, b1, W2, b2, gamma, beta, drop_p: float, site: int):
+    """LN(dropout(W2 gelu(W1 x + b1) + b2) + x) (GELU(erf) intermediate activation)."""
+    spec = types.SimpleNamespace(drop_p=float(drop_p), site=site, out_planes=None)
+    z = FFNFn.apply(x, W1, b1, W2, b2, gamma, beta, spec)
+    attach_planes(z, spec.out_planes)
+    return z
 
 
 class BiAttentionFn(Function):
