@@ -8,8 +8,8 @@
 // count of the 128x128 tiling with 25 % fewer operand bytes per FLOP, PAIR_N = 256 halves the bytes per FLOP.
 //
 // One cluster of 2 CTAs per pair tile, 320 threads per CTA:
-//   warp 0   : TMA producer (one lane, both CTAs) -- own A rows + own half of B into a 3- or 6-stage ring of 32 KB
-//              stages; every load signals the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 0   : TMA producer (one lane, both CTAs) -- own A rows + own half of B into a ring of 48 KB (PAIR_N 128)
+//              or 64 KB (256) stages filling shared memory; every load signals the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2)
 //   warp 1   : TMEM allocation (cta_group::2, both CTAs); the leader's lane 0 issues every MMA and commits with
 //              multicast arrives to the empty / accumulator-full barriers of both CTAs
 //   warps 2-9: epilogue of this CTA's 128 rows x PAIR_N columns (same fused epilogue as yv_gemm.cu)
@@ -17,20 +17,30 @@
 
 namespace {
 
+#ifndef YV_PAIR_BLOCK_K
+#define YV_PAIR_BLOCK_K 64
+#endif
 constexpr int BLOCK_M = 128;                                  // rows per CTA; the pair tile covers 256
-constexpr int BLOCK_K = 32;                                   // 64 B rows, 64B swizzle for K-major tiles
+constexpr int BLOCK_K = YV_PAIR_BLOCK_K;                      // 64: 128 B rows / 128B swizzle (TMA moves ~1 row per 1.5 clk,
+                                                              // so wide rows matter); 32: 64 B rows / 64B swizzle
+constexpr int KMAJ_LAYOUT = BLOCK_K == 32 ? 4 : 2;            // UMMA layout type of K-major tiles (SWIZZLE_64B / _128B)
+constexpr int KMAJ_SBO = BLOCK_K * 2 * 8;                     // 8 rows of BLOCK_K bf16
+constexpr int MN_CHUNK = BLOCK_K * 128;                       // MN-major: 64 m/n-elements (128 B) x BLOCK_K k-rows
 constexpr int UMMA_K = 16;
-constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // 8 KB: one plane of 128 rows x 32 k
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 2;             // one plane of 128 rows x BLOCK_K k
 constexpr int NUM_THREADS = 320;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int MAX_STAGES = 6;
-constexpr int KMAJ_SBO = BLOCK_K * 2 * 8;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 232448;                            // 227 KB of dynamic shared memory per CTA
 
 template <int PASSES>
 struct PCfg {
     static constexpr int PLANES = PASSES == 3 ? 2 : 1;
-    static constexpr int STAGE_BYTES = PLANES * 2 * TILE_BYTES;   // A_hi, B_hi, (A_lo, B_lo); B slots hold <= 128 rows
-    static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
+    // one stage = per plane: this CTA's 128 rows of A, then its half (pair_n / 2 rows) of B
+    static constexpr int stage_bytes(int pair_n) { return PLANES * (TILE_BYTES + (pair_n / 2) * BLOCK_K * 2); }
+    static constexpr int smem_bytes(int stages, int pair_n) {
+        return stages * stage_bytes(pair_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+    }
 };
 
 YV_DEVINL uint32_t cluster_ctarank() {
@@ -73,7 +83,7 @@ YV_DEVINL void umma2_commit(uint32_t bar) {
 }
 
 template <int PASSES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, BLOCK_K == 32 ? 2 : 1)
 yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ KParams p) {
     using C = PCfg<PASSES>;
@@ -81,8 +91,12 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // identical carve-up in both CTAs: the MMA descriptors and the multicast commits address the peer by offset
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * C::STAGE_BYTES);
-    // bars: [0,6) full (used in the leader only), [6,12) empty, 12 accumulator full; then the TMEM base address word
+    const int pair_n = p.pair_n;
+    const int nb_half = pair_n >> 1;                             // B rows staged by each CTA
+    const uint32_t a_bytes = TILE_BYTES, b_bytes = (uint32_t)(nb_half * BLOCK_K * 2);
+    const uint32_t plane_bytes = a_bytes + b_bytes, stage_bytes = C::PLANES * plane_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + p.stages * stage_bytes);
+    // bars: [0,8) full (used in the leader only), [8,16) empty, 16 accumulator full; then the TMEM base address word
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -92,8 +106,6 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int pair_n = p.pair_n;
-    const int nb_half = pair_n >> 1;                             // B rows staged by each CTA
     const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int tiles_n = (p.N + pair_n - 1) / pair_n;
     const int tiles_mp = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
@@ -138,31 +150,31 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0) {
         // ===================================== TMA producer (both CTAs) ==========================
         if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)(C::PLANES * (TILE_BYTES + nb_half * BLOCK_K * 2));
+            const uint32_t tx_bytes = stage_bytes;
             const int nb0_row = n0 + (int)rank * nb_half;                  // first B row staged by this CTA
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t sbase = smem_base + stage * stage_bytes;
                 const uint32_t lbar = mapa_rank(full_bar(stage), 0);       // the leader's barrier collects both CTAs' bytes
                 if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * tx_bytes);
                 const int k0 = (kb_lo + kb) * BLOCK_K;
 #pragma unroll
                 for (int pl = 0; pl < C::PLANES; ++pl) {
-                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
-                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
+                    const uint32_t sa = sbase + pl * plane_bytes;
+                    const uint32_t sb = sa + a_bytes;
                     if (!p.a_mn) {
                         tma_load_5d_pair(sa, &map_a, lbar, k0, m0, b0, b1, pl);
                     } else {
                         tma_load_5d_pair(sa, &map_a, lbar, m0, k0, b0, b1, pl);
-                        tma_load_5d_pair(sa + TILE_BYTES / 2, &map_a, lbar, m0 + 64, k0, b0, b1, pl);
+                        tma_load_5d_pair(sa + MN_CHUNK, &map_a, lbar, m0 + 64, k0, b0, b1, pl);
                     }
                     if (!p.b_mn) {
                         tma_load_5d_pair(sb, &map_b, lbar, k0, nb0_row, b0, b1, pl);
                     } else {
                         tma_load_5d_pair(sb, &map_b, lbar, nb0_row, k0, b0, b1, pl);
-                        if (nb_half > 64) tma_load_5d_pair(sb + TILE_BYTES / 2, &map_b, lbar, nb0_row + 64, k0, b0, b1, pl);
+                        if (nb_half > 64) tma_load_5d_pair(sb + MN_CHUNK, &map_b, lbar, nb0_row + 64, k0, b0, b1, pl);
                     }
                 }
                 if (++stage == p.stages) {
@@ -186,14 +198,14 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(full_bar(stage), phase);
                 if (kb == 0) YV_T(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sbase = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t sbase = smem_base + stage * stage_bytes;
                 uint64_t da[2], db[2];
 #pragma unroll
                 for (int pl = 0; pl < C::PLANES; ++pl) {
-                    const uint32_t sa = sbase + (pl * 2 + 0) * TILE_BYTES;
-                    const uint32_t sb = sbase + (pl * 2 + 1) * TILE_BYTES;
-                    da[pl] = p.a_mn ? make_desc(sa, TILE_BYTES / 2, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, 4);
-                    db[pl] = p.b_mn ? make_desc(sb, TILE_BYTES / 2, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, 4);
+                    const uint32_t sa = sbase + pl * plane_bytes;
+                    const uint32_t sb = sa + a_bytes;
+                    da[pl] = p.a_mn ? make_desc(sa, MN_CHUNK, 1024, 2) : make_desc(sa, 16, KMAJ_SBO, KMAJ_LAYOUT);
+                    db[pl] = p.b_mn ? make_desc(sb, MN_CHUNK, 1024, 2) : make_desc(sb, 16, KMAJ_SBO, KMAJ_LAYOUT);
                 }
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -332,24 +344,27 @@ extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
     const long long total_pairs = (long long)pairs * batch * p.splits;
     YV_CHECK(2 * total_pairs < 2147483647LL, "yv_gemm: too many tiles");
     p.total_tiles = (int)total_pairs;
-    // one resident CTA per SM can afford the deep ring (more bytes in flight per SM); beyond that two CTAs share an SM
-    p.stages = 2 * total_pairs <= 148 ? MAX_STAGES : 3;
+    // as many ring stages as shared memory holds (one CTA per SM); the 32-deep build keeps 3 stages on multi-wave
+    // launches so that two CTAs share an SM
+    const int stage_b = g->passes == 3 ? PCfg<3>::stage_bytes(pair_n) : PCfg<1>::stage_bytes(pair_n);
+    int stages = (SMEM_LIMIT - 1024 - 256) / stage_b;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (BLOCK_K == 32 && 2 * total_pairs > 148 && stages > 3) stages = 3;
+    p.stages = stages;
     dim3 grid((unsigned)(2 * total_pairs), 1, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p.splits > 1)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
     static bool attr_set = false;
     if (!attr_set) {
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     PCfg<1>::smem_bytes(MAX_STAGES)));
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     PCfg<3>::smem_bytes(MAX_STAGES)));
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr_set = true;
     }
     if (g->passes == 3)
-        YV_CUDA(yv_launch(yv_gemm_pair_kernel<3>, grid, dim3(NUM_THREADS), PCfg<3>::smem_bytes(p.stages), st, ma, mb, p));
+        YV_CUDA(yv_launch(yv_gemm_pair_kernel<3>, grid, dim3(NUM_THREADS), PCfg<3>::smem_bytes(p.stages, pair_n), st, ma, mb, p));
     else
-        YV_CUDA(yv_launch(yv_gemm_pair_kernel<1>, grid, dim3(NUM_THREADS), PCfg<1>::smem_bytes(p.stages), st, ma, mb, p));
+        YV_CUDA(yv_launch(yv_gemm_pair_kernel<1>, grid, dim3(NUM_THREADS), PCfg<1>::smem_bytes(p.stages, pair_n), st, ma, mb, p));
     YV_CUDA(cudaGetLastError());
     yv_count_launch();
     return 0;

@@ -107,16 +107,19 @@ class _Chunk:
         self.table = None
         self.total_blocks = 0
         self.nseg = 0
+        self.ready = None              # event of an in-flight refresh on the refresh stream (None: nothing pending)
+        self.joined = set()            # streams that already wait for `ready`
 
 
 class WeightArena:
-    CHUNK = 96 * 1024 * 1024  # elements per plane
+    CHUNK = 24 * 1024 * 1024  # elements per plane and chunk (one yv_split_multi launch, ~30 us, per chunk)
 
     def __init__(self, device):
         self.device = device
         self.chunks: List[_Chunk] = []
         self.entries: Dict[Tuple[int, ...], _Entry] = {}
         self.always_stale = False      # bench: convert weights every step as real training would
+        self.refresh_stream = None     # created on first overlapped refresh
 
     def _alloc(self, n: int) -> Tuple[_Chunk, int]:
         n_al = (n + 63) // 64 * 64
@@ -157,6 +160,12 @@ class WeightArena:
             e.chunk.entries.append(e)
             e.chunk.table = None
             self.entries[key] = e
+        c = e.chunk
+        if c.ready is not None:        # this chunk is being re-split on the refresh stream: order this stream after it
+            cur = torch.cuda.current_stream(self.device)
+            if cur.cuda_stream not in c.joined:
+                cur.wait_event(c.ready)
+                c.joined.add(cur.cuda_stream)
         if not self._fresh(e):
             self._refresh_entry(e)
         return e.planes
@@ -171,10 +180,25 @@ class WeightArena:
             r0 += p.shape[0]
         self._mark(e)
 
-    def refresh_all(self, force: bool = False):
-        """Re-split every chunk that holds a stale entry with one ``yv_split_multi`` launch."""
-        force = force or self.always_stale
+    def join(self):
+        """Order the current stream after every in-flight refresh (end of the forward pass / of a captured step)."""
+        if self.refresh_stream is not None and any(c.ready is not None for c in self.chunks):
+            torch.cuda.current_stream(self.device).wait_stream(self.refresh_stream)
         for c in self.chunks:
+            c.ready = None
+            c.joined = set()
+
+    def refresh_all(self, force: bool = False, overlap: bool = False):
+        """Re-split every chunk that holds a stale entry with one ``yv_split_multi`` launch.  With ``overlap`` the
+        chunks after the first (the arena is filled in forward order, so they hold the later layers) are converted on
+        a separate stream while the forward pass starts; ``get`` orders each consumer stream after its chunk."""
+        force = force or self.always_stale
+        cur = torch.cuda.current_stream(self.device)
+        if overlap and len(self.chunks) > 1:
+            if self.refresh_stream is None:
+                self.refresh_stream = torch.cuda.Stream(device=self.device)
+            self.refresh_stream.wait_stream(cur)
+        for ci, c in enumerate(self.chunks):
             if not c.entries:
                 continue
             if not force and all(self._fresh(e) for e in c.entries):
@@ -196,7 +220,14 @@ class WeightArena:
                 c.table = (t, ptrs)
                 c.total_blocks = blk
                 c.nseg = len(rows)
-            L.split_multi(c.table[0], c.nseg, c.total_blocks, c.buf, c.cap)
+            if overlap and ci > 0 and self.refresh_stream is not None:
+                with torch.cuda.stream(self.refresh_stream):
+                    L.split_multi(c.table[0], c.nseg, c.total_blocks, c.buf, c.cap)
+                    c.ready = torch.cuda.Event()
+                    c.ready.record(self.refresh_stream)
+                c.joined = set()
+            else:
+                L.split_multi(c.table[0], c.nseg, c.total_blocks, c.buf, c.cap)
             for e in c.entries:
                 self._mark(e)
 

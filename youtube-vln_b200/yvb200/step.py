@@ -172,12 +172,14 @@ class GraphedStep:
     def _body(self):
         self.rt.advance_rng()
         if self.refresh:
-            self.rt.arena.refresh_all(force=True)
+            # chunk 0 (first layers) on this stream, the rest overlapped with the start of the forward pass
+            self.rt.arena.refresh_all(force=True, overlap=self.rt.concurrent)
         b = self.static
         co = b[11]
         inputs = (b[6].flatten(0, 1), b[1].flatten(0, 1), b[2].flatten(0, 1), b[10].flatten(0, 1), b[7].flatten(0, 1),
                   b[3].flatten(0, 1), co.reshape(-1, co.size(2), co.size(3)), b[9].flatten(0, 1), b[15])
         out = self.model(*inputs)
+        self.rt.arena.join()
         ld = fused.step_losses(b, out, self.args, training=True, flat=True)
         tot = 0.0
         for k in ("vision", "language", "ranking"):
