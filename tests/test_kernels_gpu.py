@@ -204,8 +204,8 @@ def test_gemm_batched_head_views(L):
     assert _rel(ctx.float(), ref) < 3e-5
 
 
-def test_layernorm_fwd_bwd(L):
-    M, Cd = 300, 768
+@pytest.mark.parametrize("M,Cd", [(300, 768), (2304, 1024), (37, 64), (9, 32), (130, 200), (641, 512)])
+def test_layernorm_fwd_bwd(L, M, Cd):
     x = _mk(M, Cd, 20).requires_grad_(True)
     g = (1 + 0.1 * _mk(1, Cd, 21)[0]).contiguous().requires_grad_(True)
     b = (0.1 * _mk(1, Cd, 22)[0]).contiguous().requires_grad_(True)

@@ -52,11 +52,12 @@ def chain_ln(M, C, n=20):
         for i in range(n): L.split_planes(x, yp)
     print(f"M={M} C={C}: ln_fwd {graph_time(f1)/n:.1f} us, ln_bwd {graph_time(f2)/n:.1f} us, colsum_planes {graph_time(f3)/n:.1f} us, split {graph_time(f4)/n:.1f} us")
 
-chain_gemm(2304, 1024, 1024)
-chain_gemm(2304, 1024, 1024, full_epi=False)
-chain_gemm(2304, 1024, 1024, passes=1)
-chain_gemm(640, 768, 768)
-chain_gemm(640, 768, 768, passes=1)
-chain_gemm(128, 128, 128)
+if "ln" not in sys.argv:
+    chain_gemm(2304, 1024, 1024)
+    chain_gemm(2304, 1024, 1024, full_epi=False)
+    chain_gemm(2304, 1024, 1024, passes=1)
+    chain_gemm(640, 768, 768)
+    chain_gemm(640, 768, 768, passes=1)
+    chain_gemm(128, 128, 128)
 chain_ln(2304, 1024)
 chain_ln(640, 768)

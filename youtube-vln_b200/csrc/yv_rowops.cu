@@ -339,6 +339,179 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// LayerNorm, warp-per-row variants (default).  A row (C <= 1024) lives in the registers of one warp: lane l owns the
+// float4 column groups l, l + 32, ... so every access is a 512-byte coalesced warp transaction and the row statistics
+// need warp shuffles only -- no shared memory, no block barrier on the dependency chain of the step.
+// ------------------------------------------------------------------------------------------------
+constexpr int LNW_WARPS = 8;      // rows in flight per block
+constexpr int LNW_MAXV = 8;       // float4 groups per lane: C <= 32 * 4 * 8 = 1024
+
+template <int NV>
+__global__ void __launch_bounds__(LNW_WARPS * 32)
+layernorm_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yp, long long plane_stride,
+                          float* __restrict__ stats, long long M, int C, float drop_p, unsigned drop_site,
+                          const unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = blockIdx.x * (long long)LNW_WARPS + warp;
+    if (row >= M) return;
+    const float* xr = x + row * C;
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        v[j] = c < C ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = yv_warp_sum(sum) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c < C) {
+            const float a = v[j].x - mean, b = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+            q += (a * a + b * b) + (d * d + e * e);
+        }
+    }
+    const float rstd = 1.f / sqrtf(yv_warp_sum(q) / C + eps);
+    if (stats && lane == 0) {
+        stats[2 * row] = mean;
+        stats[2 * row + 1] = rstd;
+    }
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        if (c >= C) continue;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float o[4] = {g4.x * ((v[j].x - mean) * rstd) + b4.x, g4.y * ((v[j].y - mean) * rstd) + b4.y,
+                      g4.z * ((v[j].z - mean) * rstd) + b4.z, g4.w * ((v[j].w - mean) * rstd) + b4.w};
+        if (drop.thresh) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] *= yv_drop_mul(drop, (uint32_t)(row * C + c + e));
+        }
+        if (y32) *reinterpret_cast<float4*>(y32 + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (yp) {
+            __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) yv_split(o[e], h4[e], l4[e]);
+            *reinterpret_cast<uint2*>(yp + row * C + c) = *reinterpret_cast<uint2*>(h4);
+            *reinterpret_cast<uint2*>(yp + plane_stride + row * C + c) = *reinterpret_cast<uint2*>(l4);
+        }
+    }
+}
+
+// Backward: each warp walks rows (grid-stride over warps); the column sums dgamma / dbeta / dbias stay in registers per
+// lane, are combined across the block's warps through shared memory and leave as one vector reduction per block and
+// column group.
+template <int NV>
+__global__ void __launch_bounds__(LNW_WARPS * 32)
+layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                          const float* __restrict__ stats, float post_p, unsigned post_site,
+                          const float* __restrict__ dx_add, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxp,
+                          long long plane_stride, float pre_p, unsigned pre_site, const unsigned long long* rng,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, long long M,
+                          int C) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    __shared__ float4 red[LNW_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const YvDrop dpost = yv_drop_make(rng, post_site, post_p);
+    const YvDrop dpre = yv_drop_make(rng, pre_site, pre_p);
+    float4 gm[NV], ag[NV], ab[NV], abias[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 4;
+        gm[j] = c < C ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ag[j] = ab[j] = abias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float invC = 1.f / C;
+    const long long nwarps = (long long)gridDim.x * LNW_WARPS;
+    for (long long row = blockIdx.x * (long long)LNW_WARPS + warp; row < M; row += nwarps) {
+        const float mean = stats[2 * row], rs = stats[2 * row + 1];
+        float4 g[NV], xh[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            g[j] = xh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) {
+                float4 d = *reinterpret_cast<const float4*>(dy + row * C + c);
+                const float4 xv = *reinterpret_cast<const float4*>(x + row * C + c);
+                if (dpost.thresh) {
+                    const uint32_t i0 = (uint32_t)(row * C + c);
+                    d.x *= yv_drop_mul(dpost, i0); d.y *= yv_drop_mul(dpost, i0 + 1);
+                    d.z *= yv_drop_mul(dpost, i0 + 2); d.w *= yv_drop_mul(dpost, i0 + 3);
+                }
+                xh[j] = make_float4((xv.x - mean) * rs, (xv.y - mean) * rs, (xv.z - mean) * rs, (xv.w - mean) * rs);
+                ag[j].x += d.x * xh[j].x; ag[j].y += d.y * xh[j].y; ag[j].z += d.z * xh[j].z; ag[j].w += d.w * xh[j].w;
+                ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
+                g[j] = make_float4(d.x * gm[j].x, d.y * gm[j].y, d.z * gm[j].z, d.w * gm[j].w);
+                s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+                s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+            }
+        }
+        s1 = yv_warp_sum(s1) * invC;
+        s2 = yv_warp_sum(s2) * invC;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 4;
+            if (c >= C) continue;
+            float o[4] = {rs * (g[j].x - s1 - xh[j].x * s2), rs * (g[j].y - s1 - xh[j].y * s2),
+                          rs * (g[j].z - s1 - xh[j].z * s2), rs * (g[j].w - s1 - xh[j].w * s2)};
+            if (dx_add) {
+                const float4 a4 = *reinterpret_cast<const float4*>(dx_add + row * C + c);
+                o[0] += a4.x; o[1] += a4.y; o[2] += a4.z; o[3] += a4.w;
+            }
+            if (dx32) *reinterpret_cast<float4*>(dx32 + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+            if (dpre.thresh) {
+                const uint32_t i0 = (uint32_t)(row * C + c);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] *= yv_drop_mul(dpre, i0 + e);
+            }
+            abias[j].x += o[0]; abias[j].y += o[1]; abias[j].z += o[2]; abias[j].w += o[3];
+            if (dxp) {
+                __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) yv_split(o[e], h4[e], l4[e]);
+                *reinterpret_cast<uint2*>(dxp + row * C + c) = *reinterpret_cast<uint2*>(h4);
+                *reinterpret_cast<uint2*>(dxp + plane_stride + row * C + c) = *reinterpret_cast<uint2*>(l4);
+            }
+        }
+    }
+    // block-level column sums: one array and one column group at a time through 4 KB of shared memory
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+        float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+        if (out == nullptr) continue;                        // block-uniform
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (j * 128 >= C) break;                         // block-uniform
+            red[warp][lane] = which == 0 ? ag[j] : (which == 1 ? ab[j] : abias[j]);
+            __syncthreads();
+            if (warp == 0) {
+                float4 t = red[0][lane];
+#pragma unroll
+                for (int w = 1; w < LNW_WARPS; ++w) {
+                    const float4 u = red[w][lane];
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                const int c = (j * 32 + lane) * 4;
+                if (c < C)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c), "f"(t.x), "f"(t.y),
+                                 "f"(t.z), "f"(t.w)
+                                 : "memory");
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // attention softmax
 // ------------------------------------------------------------------------------------------------
 // one warp per row, the row lives in registers (cols <= 32 * MAXPL): one read and one write of the scores
@@ -773,6 +946,9 @@ kl_grad_kernel(const float* __restrict__ logits, long long ld, const float* __re
 }
 
 inline cudaStream_t S(yv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+// YVB200_LN=block selects the older block-per-4-rows LayerNorm kernels (kept for A/B timing)
+const bool g_ln_warp = []() { const char* e = getenv("YVB200_LN"); return !(e && e[0] == 'b'); }();
+
 inline int grid_for(long long n, int per_block, int cap = 148 * 16) {
     long long g = (n + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -826,6 +1002,17 @@ extern "C" int yv_layernorm_fwd(const float* x, const float* gamma, const float*
     YV_CHECK(((((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)y32) & 15) == 0) &&
                  ((((uintptr_t)y_planes) & 7) == 0) && (plane_stride % 4 == 0),
              "yv_layernorm_fwd: pointers must be 16-byte aligned");
+    if (g_ln_warp) {
+        const dim3 grid((unsigned)((M + LNW_WARPS - 1) / LNW_WARPS)), block(LNW_WARPS * 32);
+        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_planes);
+        const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+        const int nv = (C + 127) / 128;
+#define YV_LNF(NV) YV_CUDA(yv_launch(layernorm_fwd_warp_kernel<NV>, grid, block, 0, S(stream), x, gamma, beta, eps, y32, yp, \
+                                     plane_stride, stats, M, C, drop_p, drop_site, r))
+        if (nv <= 2) YV_LNF(2); else if (nv <= 4) YV_LNF(4); else if (nv <= 6) YV_LNF(6); else YV_LNF(8);
+#undef YV_LNF
+        YV_LAUNCHED();
+    }
     const int threads = ((C / 4 + 31) / 32) * 32;
     YV_CUDA(yv_launch(layernorm_fwd_kernel, dim3((unsigned)((M + LNF_ROWS - 1) / LNF_ROWS)), dim3(threads), 0, S(stream), x, gamma,
                       beta, eps, y32, reinterpret_cast<__nv_bfloat16*>(y_planes), plane_stride, stats, M, C, drop_p, drop_site,
@@ -843,6 +1030,19 @@ extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* ga
                 (uintptr_t)dbeta | (uintptr_t)dbias) & 15) == 0) && ((((uintptr_t)dx_planes) & 7) == 0) &&
                  (plane_stride % 4 == 0),
              "yv_layernorm_bwd: pointers must be 16-byte aligned");
+    if (g_ln_warp) {
+        // at most one block per SM: every block ends with 3 * C / 4 vector reductions into dgamma / dbeta / dbias
+        const dim3 grid((unsigned)grid_for(M, LNW_WARPS, 148)), block(LNW_WARPS * 32);
+        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dx_planes);
+        const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+        const int nv = (C + 127) / 128;
+#define YV_LNB(NV) YV_CUDA(yv_launch(layernorm_bwd_warp_kernel<NV>, grid, block, 0, S(stream), dy, x, gamma, stats, post_drop_p, \
+                                     post_drop_site, dx_add, dx32, dp, plane_stride, pre_drop_p, pre_drop_site, r, dgamma, dbeta, \
+                                     dbias, M, C))
+        if (nv <= 2) YV_LNB(2); else if (nv <= 4) YV_LNB(4); else if (nv <= 6) YV_LNB(6); else YV_LNB(8);
+#undef YV_LNB
+        YV_LAUNCHED();
+    }
     const int threads = ((C / 4 + 31) / 32) * 32;
     const int grid = grid_for(M, LNB_ROWS, 148 * 4);
     YV_CUDA(yv_launch(layernorm_bwd_kernel, dim3(grid), dim3(threads), 0, S(stream), dy, x, gamma, stats, post_drop_p, post_drop_site, dx_add, dx32,

@@ -58,14 +58,20 @@ class Runtime:
         # captured step graph has parallel branches; YVB200_CONCURRENT=0 serialises everything on one stream
         self.concurrent = os.environ.get("YVB200_CONCURRENT", "1") != "0"
         self._helpers: Dict[int, torch.cuda.Stream] = {}
-        self.branch_stream = torch.cuda.Stream(device=device)
+        # stream priorities (retained as kernel-node priorities when the step is captured): the two stream-level
+        # branches (text / vision) carry the critical dependency chain and run at high priority; helper streams
+        # carry work nobody waits for until the end of a block (weight gradients, bias gradients) and fill in behind
+        prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
+        self.main_priority = -1 if prio else 0
+        self.helper_priority = 0
+        self.branch_stream = torch.cuda.Stream(device=device, priority=self.main_priority)
 
     def helper(self) -> torch.cuda.Stream:
         """The helper stream paired with the current stream (created on first use)."""
         cur = torch.cuda.current_stream(self.device)
         h = self._helpers.get(cur.cuda_stream)
         if h is None:
-            h = self._helpers[cur.cuda_stream] = torch.cuda.Stream(device=self.device)
+            h = self._helpers[cur.cuda_stream] = torch.cuda.Stream(device=self.device, priority=self.helper_priority)
         return h
 
     def set_precision(self, mode: str):

@@ -26,8 +26,11 @@ class GradientExchange:
     The reference gets the same overlap from ``DistributedDataParallel`` bucket hooks (utils/distributed.py:97-99).
     """
 
-    def __init__(self, model: torch.nn.Module, group=None, segment_mb: float = 160.0, overlap: bool = True):
+    def __init__(self, model: torch.nn.Module, group=None, segment_mb: float = None, overlap: bool = True):
+        import os
         import torch.distributed as dist
+        if segment_mb is None:
+            segment_mb = float(os.environ.get("YVB200_SEGMENT_MB", "160"))
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group)
         self.segment_bytes = int(segment_mb * 2 ** 20)
@@ -144,7 +147,7 @@ class GraphedStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.use_graph = use_graph
-        side = torch.cuda.Stream(device=self.device)
+        side = torch.cuda.Stream(device=self.device, priority=self.rt.main_priority)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -156,7 +159,7 @@ class GraphedStep:
             self._zero_grads()
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.launch_count()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._body()
             self.launches_per_step = lib.launch_count() - n0
         else:
