@@ -57,22 +57,71 @@ class Runtime:
         # independent work (dgrad vs wgrad, text vs vision stream) is issued on helper CUDA streams so that the
         # captured step graph has parallel branches; YVB200_CONCURRENT=0 serialises everything on one stream
         self.concurrent = os.environ.get("YVB200_CONCURRENT", "1") != "0"
-        self._helpers: Dict[int, torch.cuda.Stream] = {}
+        self._helpers: Dict[Tuple[int, int], torch.cuda.Stream] = {}
+        self._helper_pool: Dict[int, List[torch.cuda.Stream]] = {}
+        self._helper_next: Dict[int, int] = {}
+        self._forks: Dict[Tuple[int, int], torch.cuda.Stream] = {}
+        self.helpers_per_stream = int(os.environ.get("YVB200_HELPERS", "1"))   # measured: 1 best (2: +0.15 ms)
         # stream priorities (retained as kernel-node priorities when the step is captured): the two stream-level
         # branches (text / vision) carry the critical dependency chain and run at high priority; helper streams
         # carry work nobody waits for until the end of a block (weight gradients, bias gradients) and fill in behind
+        # weight / bias gradients of the encoder layers are not joined back into the dependency chain of the backward
+        # pass: they trail on the helper streams and are joined once at the end (YVB200_DEFER_WGRAD=0: join at once)
+        self.defer_wgrad = os.environ.get("YVB200_DEFER_WGRAD", "1") != "0"
+        self._join_queued = False
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
         self.main_priority = -1 if prio else 0
         self.helper_priority = 0
         self.branch_stream = torch.cuda.Stream(device=device, priority=self.main_priority)
 
-    def helper(self) -> torch.cuda.Stream:
-        """The helper stream paired with the current stream (created on first use)."""
+    # ---- deferred weight-gradient work -------------------------------------------------------------
+    def defer_join(self):
+        """Called by a backward that left work running on a helper stream: all helper streams are joined into the
+        stream that called ``backward()`` once, by an autograd-engine callback at the end of the backward pass."""
+        if not self._join_queued:
+            self._join_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._final_join)
+
+    def _final_join(self):
+        self._join_queued = False
         cur = torch.cuda.current_stream(self.device)
-        h = self._helpers.get(cur.cuda_stream)
-        if h is None:
-            h = self._helpers[cur.cuda_stream] = torch.cuda.Stream(device=self.device, priority=self.helper_priority)
-        return h
+        capturing = torch.cuda.is_current_stream_capturing()
+        for s_ in [self.branch_stream] + list(self._helpers.values()):
+            if s_ == cur:
+                continue
+            if capturing:                                   # only streams that belong to this capture can be joined
+                with torch.cuda.stream(s_):
+                    if not torch.cuda.is_current_stream_capturing():
+                        continue
+            cur.wait_stream(s_)
+
+    def fork(self, slot: int = 0) -> torch.cuda.Stream:
+        """Stream for a short branch that is joined again at once (slot 0: the second attention direction or a weight
+        gradient that is not deferred; slot 1: dV / dK inside an attention backward): same priority as the chain,
+        never shared with trailing work."""
+        cur = torch.cuda.current_stream(self.device)
+        key = (cur.cuda_stream, slot)
+        f = self._forks.get(key)
+        if f is None:
+            f = self._forks[key] = torch.cuda.Stream(device=self.device, priority=self.main_priority)
+            self._helpers[(cur.cuda_stream, -1 - slot)] = f   # joined with the helpers at segment / pass ends
+        return f
+
+    def helper(self) -> torch.cuda.Stream:
+        """A trailing-work stream paired with the current stream (created on first use).  With deferred weight gradients
+        the helpers of a stream are handed out round-robin so that several small trailing GEMMs can be in flight."""
+        cur = torch.cuda.current_stream(self.device)
+        pool = self._helper_pool.get(cur.cuda_stream)
+        if pool is None:
+            n = self.helpers_per_stream if self.defer_wgrad else 1
+            pool = self._helper_pool[cur.cuda_stream] = [
+                torch.cuda.Stream(device=self.device, priority=self.helper_priority) for _ in range(n)]
+            for i, h in enumerate(pool):
+                self._helpers[(cur.cuda_stream, i)] = h
+            self._helper_next[cur.cuda_stream] = 0
+        i = self._helper_next[cur.cuda_stream]
+        self._helper_next[cur.cuda_stream] = (i + 1) % len(pool)
+        return pool[i]
 
     def set_precision(self, mode: str):
         self.passes = 3 if mode == "bf16x3" else 1
@@ -275,11 +324,22 @@ def _f32(*shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+def _keep_for(side: torch.cuda.Stream, *objs):
+    """Tensors consumed (or produced) by work left running on ``side``: the caching allocator must not hand their
+    memory to a later allocation of the issuing stream before that work has run."""
+    for o in objs:
+        if o is None:
+            continue
+        t = o.keep if isinstance(o, Planes) else o
+        t.record_stream(side)
+
+
 def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int, N: int, K: int, device,
                 need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None,
-                db: Optional[torch.Tensor] = None):
+                db: Optional[torch.Tensor] = None, defer: bool = False):
     """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K].
-    ``db`` may arrive precomputed (fused into the kernel that produced ``dp``)."""
+    ``db`` may arrive precomputed (fused into the kernel that produced ``dp``).  With ``defer`` the weight / bias
+    gradient is left running on the helper stream (joined at the end of the backward pass, see Runtime.defer_join)."""
     dx = dW = None
     have_db = db is not None
     if need_dx:
@@ -291,14 +351,19 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
     fork = r.concurrent and need_dx and need_dw
     if fork:                                    # wgrad + bias grad on the helper stream, dgrad on this one
         cur = torch.cuda.current_stream(device)
-        side = r.helper()
+        trailing = defer and r.defer_wgrad
+        side = r.helper() if trailing else r.fork()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
             if not have_db:
                 L.colsum_planes(dp, db)
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
-        cur.wait_stream(side)
+        if trailing:
+            _keep_for(side, dp, xp, dW, None if have_db else db)
+            r.defer_join()
+        else:
+            cur.wait_stream(side)
         return dx, dW, db
     if need_dx:
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
@@ -399,7 +464,7 @@ class DenseResLNFn(Function):
         L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, N, pre_drop_p=spec.drop_p,
                         pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
         dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2],
-                                 db=acc[2])
+                                 db=acc[2], defer=True)
         return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, acc[0], acc[1], None
 
 
@@ -499,32 +564,45 @@ def _attn_fwd(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Ten
 
 
 def _attn_bwd(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, P: torch.Tensor, Pp: Planes, pairs: int,
-              heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView):
+              heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView,
+              fork_ok: bool = True):
+    """dP -> softmax' -> dQ on the issuing stream; dV (needs only P and dO) and dK (needs dS) on a forked stream when
+    ``fork_ok`` (callers that already run this function on a forked stream pass False)."""
     Tq, Tk = q.S, k.S
     ldS = P.shape[-1]
     dev = P.device
     rows = pairs * heads * Tq
     dO = HeadView(dOp, 0, Tq)
-    # dPd = dO . V^T
-    dPd = _f32(pairs, heads, Tq, ldS, device=dev)
-    L.gemm(Tq, Tk, dh, dO.operand(pairs, heads, dh, False), v.operand(pairs, heads, dh, False), passes=r.attn_passes,
-           out32=dPd, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
+    cur = torch.cuda.current_stream(dev)
+    side = r.fork(1) if (r.concurrent and fork_ok) else cur
 
     def out_view(hv: HeadView):
         return dict(out_planes=hv.p.ptr(hv.off), ld_pl=hv.p.ld, pl_sb0=dh, pl_sb1=hv.S * hv.p.ld,
                     pl_plane_stride=hv.p.plane_stride)
 
-    # dV = Pd^T . dO     [Tk, dh], contraction over Tq
-    L.gemm(Tk, dh, Tq, _score_operand(Pp, Tq, Tk, ldS, pairs, heads, True), dO.operand(pairs, heads, dh, True),
-           passes=r.attn_passes, **out_view(dv))
+    if side is not cur:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        # dV = Pd^T . dO     [Tk, dh], contraction over Tq
+        L.gemm(Tk, dh, Tq, _score_operand(Pp, Tq, Tk, ldS, pairs, heads, True), dO.operand(pairs, heads, dh, True),
+               passes=r.attn_passes, **out_view(dv))
+    # dPd = dO . V^T
+    dPd = _f32(pairs, heads, Tq, ldS, device=dev)
+    L.gemm(Tq, Tk, dh, dO.operand(pairs, heads, dh, False), v.operand(pairs, heads, dh, False), passes=r.attn_passes,
+           out32=dPd, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
     dSp = Planes.empty(rows, Tk, dev, ld=ldS)
     L.softmax_bwd(P, dPd, ldS, rows, Tk, 1.0 / math.sqrt(dh), dSp, drop_p, site, r.rng)
+    if side is not cur:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        # dK = dS^T . Q      [Tk, dh], contraction over Tq
+        L.gemm(Tk, dh, Tq, _score_operand(dSp, Tq, Tk, ldS, pairs, heads, True), q.operand(pairs, heads, dh, True),
+               passes=r.attn_passes, **out_view(dk))
     # dQ = dS . K        [Tq, dh], contraction over Tk
     L.gemm(Tq, dh, Tk, _score_operand(dSp, Tq, Tk, ldS, pairs, heads, False), k.operand(pairs, heads, dh, True),
            passes=r.attn_passes, **out_view(dq))
-    # dK = dS^T . Q      [Tk, dh], contraction over Tq
-    L.gemm(Tk, dh, Tq, _score_operand(dSp, Tq, Tk, ldS, pairs, heads, True), q.operand(pairs, heads, dh, True),
-           passes=r.attn_passes, **out_view(dk))
+    if side is not cur:
+        cur.wait_stream(side)
 
 
 def _mask2d(mask: torch.Tensor, pairs: int, Tk: int) -> torch.Tensor:
@@ -581,7 +659,7 @@ class SelfAttentionFn(Function):
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
         _attn_bwd(r, dOp, q, k, v, P, ctx.Pp, pairs, heads, dh, spec.drop_p, spec.site,
                   HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
-        dx, dW, db = _linear_bwd(r, dqkv, ctx.xp, ctx.wp, M, 3 * H, K, dev, ctx.needs_input_grad[0], True)
+        dx, dW, db = _linear_bwd(r, dqkv, ctx.xp, ctx.wp, M, 3 * H, K, dev, ctx.needs_input_grad[0], True, defer=True)
         return ((dx.view(pairs, S, K) if dx is not None else None), None,
                 dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:], None)
 
@@ -653,7 +731,7 @@ class AttnBlockFn(Function):
         dWo = _f32(H, H, device=dev)
         dOp = Planes.empty(M, H, dev)
         cur = torch.cuda.current_stream(dev)
-        side = r.helper() if r.concurrent else cur
+        side = (r.helper() if r.defer_wgrad else r.fork()) if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):                                     # wgrad of the output projection
             L.gemm(H, H, M, L.op_of(dsp, True), L.op_of(cp, True), passes=r.passes, out32=dWo, ld_out=H)
@@ -664,9 +742,13 @@ class AttnBlockFn(Function):
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
         _attn_bwd(r, dOp, q, k, v, P, Pp, pairs, heads, dh, spec.drop_p, spec.site,
                   HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
-        cur.wait_stream(side)
+        if side is not cur and r.defer_wgrad:
+            _keep_for(side, dsp, cp, dWo)
+            r.defer_join()
+        else:
+            cur.wait_stream(side)
         need_dx = ctx.needs_input_grad[0]
-        dx, dW, db = _linear_bwd(r, dqkv, xp, wqkv, M, 3 * H, K, dev, need_dx, True, dx_residual=ds)
+        dx, dW, db = _linear_bwd(r, dqkv, xp, wqkv, M, 3 * H, K, dev, need_dx, True, dx_residual=ds, defer=True)
         if not need_dx:
             dx = None
         return ((dx.view(pairs, S, K) if dx is not None else None), None,
@@ -737,7 +819,7 @@ class FFNFn(Function):
         db1 = _f32(FF, device=dev)
         dprep = Planes.empty(M, FF, dev)
         cur = torch.cuda.current_stream(dev)
-        side = r.helper() if r.concurrent else cur
+        side = (r.helper() if r.defer_wgrad else r.fork()) if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):                                     # dW2 = ds^T . h
             L.gemm(H, FF, M, L.op_of(dsp, True), L.op_of(hp, True), passes=r.passes, out32=dW2, ld_out=FF)
@@ -752,7 +834,11 @@ class FFNFn(Function):
         if ctx.needs_input_grad[0]:                                       # dx = d(pre) . W1 + ds (residual branch)
             dx = _f32(M, H, device=dev)
             L.gemm(M, H, FF, L.op_of(dprep), L.op_of(w1, True), passes=r.passes, out32=dx, ld_out=H, residual=ds)
-        cur.wait_stream(side)
+        if side is not cur and r.defer_wgrad:
+            _keep_for(side, dsp, hp, dW2, dprep, xp, dW1, db1)
+            r.defer_join()
+        else:
+            cur.wait_stream(side)
         return ((dx.view(ctx.xshape) if dx is not None else None), dW1, db1, dW2, acc[2], acc[0], acc[1], None)
 
 
@@ -793,7 +879,7 @@ class BiAttentionFn(Function):
         q1, k1, v1 = HeadView(qkv1, 0, V), HeadView(qkv1, H, V), HeadView(qkv1, 2 * H, V)
         q2, k2, v2 = HeadView(qkv2, 0, T), HeadView(qkv2, H, T), HeadView(qkv2, 2 * H, T)
         cur = torch.cuda.current_stream(dev)
-        side = r.helper() if r.concurrent else cur
+        side = r.fork() if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             L.gemm(Mt, 3 * H, Kt, L.op_of(xtp), L.op_of(w2), passes=r.passes, bias=b2c,
@@ -833,14 +919,14 @@ class BiAttentionFn(Function):
         dq1, dk1, dv1 = HeadView(d1, 0, V), HeadView(d1, H, V), HeadView(d1, 2 * H, V)
         dq2, dk2, dv2 = HeadView(d2, 0, T), HeadView(d2, H, T), HeadView(d2, 2 * H, T)
         cur = torch.cuda.current_stream(dev)
-        side = r.helper() if r.concurrent else cur
+        side = r.fork() if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
         _attn_bwd(r, dO2, q1, k2, v2, P2, P2p, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2)
         cur.wait_stream(side)
-        dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True)
-        dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True)
+        dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True, defer=True)
+        dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True, defer=True)
         return ((dxv.view(pairs, V, Kv) if dxv is not None else None), None,
                 (dxt.view(pairs, T, Kt) if dxt is not None else None), None,
                 dW1[:H], db1[:H], dW1[H:2 * H], db1[H:2 * H], dW1[2 * H:], db1[2 * H:],
