@@ -67,8 +67,12 @@ typedef struct {
     float drop_p;                 /* dropout after the activation, before the residual add */
     uint32_t drop_site;
     const uint64_t* rng;          /* device {seed, step}; NULL or drop_p == 0 disables dropout */
+    int32_t out32_zeroed;         /* the caller already zero-filled out32 (split-K launches skip their memset node) */
+    int32_t _pad2;
 } YvGemm;
 int yv_gemm(const YvGemm* g, yv_stream_t stream);
+/* number of K splits yv_gemm would use for this problem (1 = none); lets a caller zero-fill the output early */
+int yv_gemm_splits(const YvGemm* g);
 /* Tuning / test knob (process-wide, not thread-safe): which kernel yv_gemm launches.  0 = automatic (default),
  * 32 / 64 = one CTA per 128x128 tile (half-SM ring / persistent), 2 = CTA pairs (tcgen05 cta_group::2, 256-row
  * pair tiles, width chosen per problem), 128 / 256 = CTA pairs with that tile width. */

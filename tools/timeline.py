@@ -74,3 +74,16 @@ for t, d, nm in events:
     last = t
     active[fam(nm)] += d
 print("time running alone (ms):", {k: round(v / 1e3, 3) for k, v in alone.most_common(12)})
+
+# per-stream view: kernels, busy time, and the gaps between consecutive kernels of the busiest streams
+by_stream = collections.defaultdict(list)
+for e in ks:
+    by_stream[e["args"].get("stream", -1)].append(e)
+print("streams:")
+for sid, evs in sorted(by_stream.items(), key=lambda kv: -sum(e["dur"] for e in kv[1]))[:8]:
+    evs.sort(key=lambda e: e["ts"])
+    busy_s = sum(e["dur"] for e in evs)
+    gaps = [evs[i + 1]["ts"] - (evs[i]["ts"] + evs[i]["dur"]) for i in range(len(evs) - 1)]
+    small = [g for g in gaps if 0 <= g < 20]
+    print(f"  stream {sid}: {len(evs):4d} kernels, busy {busy_s/1e3:7.3f} ms, first {(evs[0]['ts']-t0)/1e3:7.3f} last {(evs[-1]['ts']+evs[-1]['dur']-t0)/1e3:7.3f} ms, "
+          f"median gap {sorted(gaps)[len(gaps)//2] if gaps else 0:.1f} us, sum of gaps<20us {sum(small)/1e3:.3f} ms")

@@ -274,11 +274,21 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
-const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
-
 }  // namespace
 
 void yv_count_launch();
+
+#if YV_BLOCK_K == 32
+#define YV_GEMM_SPLITS yv_gemm_k32_splits
+#else
+#define YV_GEMM_SPLITS yv_gemm_k64_splits
+#endif
+// number of K splits YV_GEMM_ENTRY would use for this problem (the caller may pre-zero the output, see out32_zeroed)
+extern "C" int YV_GEMM_SPLITS(const YvGemm* g) {
+    const int tiles = ((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M);
+    int kbps;
+    return plan_split_k(g, tiles, (g->K + BLOCK_K - 1) / BLOCK_K, &kbps);
+}
 
 extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
     YV_CHECK(g != nullptr, "yv_gemm: NULL args");
@@ -322,23 +332,7 @@ extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
 
     const int tiles = ((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M);
     const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
-    p.splits = 1;
-    p.kb_per_split = total_kb;
-    // split-K when the tile count leaves most SMs idle and the epilogue is linear with a plain f32 output whose
-    // rows are 16-byte aligned (the output must then be zero-filled: done here with a memset node)
-    const bool linear_epi = g->act == YV_ACT_NONE && !g->aux_out && !g->out_planes && g->out32 &&
-                            (g->ld_out % 4 == 0) && (g->N % 4 == 0) && (((uintptr_t)g->out32) & 15) == 0 &&
-                            (!g->residual || g->residual != g->out32) && (!g->bias || (((uintptr_t)g->bias) & 15) == 0) &&
-                            (!g->residual || (((uintptr_t)g->residual) & 15) == 0);
-    if (a.nb0 * a.nb1 == 1 && linear_epi && tiles * 2 <= 148 && total_kb >= 8 && g_split_k) {
-        int s = 148 / tiles;
-        if (s > total_kb / 4) s = total_kb / 4;
-        if (s > 16) s = 16;
-        if (s >= 2) {
-            p.kb_per_split = (total_kb + s - 1) / s;
-            p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-        }
-    }
+    p.splits = plan_split_k(g, tiles, total_kb, &p.kb_per_split);
     const long long total_tiles = (long long)tiles * a.nb0 * a.nb1 * p.splits;
     YV_CHECK(total_tiles < 2147483647LL, "yv_gemm: too many tiles");
     p.total_tiles = (int)total_tiles;
@@ -350,7 +344,7 @@ extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
     }
     dim3 grid((unsigned)((!PERSISTENT || total_tiles < num_sms) ? total_tiles : num_sms), 1, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p.splits > 1)
+    if (p.splits > 1 && !g->out32_zeroed)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
     static bool attr_set = false;
     if (!attr_set) {

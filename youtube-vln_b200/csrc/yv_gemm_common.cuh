@@ -317,6 +317,25 @@ YV_DEVINL void epilogue_chunk(const KParams& p, const YvDrop& drop, uint32_t stg
 
 // ------------------------------------------------------------------------------------------- host
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
+
+// Split-K plan shared by the variants: split when the tile count leaves most SMs idle and the epilogue is linear with
+// a plain f32 output whose rows are 16-byte aligned (partial sums meet through vector reductions in a zero-filled
+// output).  `ctas` = CTAs the un-split problem would launch.  Returns the number of splits (1 = no split).
+inline int plan_split_k(const YvGemm* g, int ctas, int total_kb, int* kb_per_split) {
+    *kb_per_split = total_kb;
+    const bool linear_epi = g->act == YV_ACT_NONE && !g->aux_out && !g->out_planes && g->out32 &&
+                            (g->ld_out % 4 == 0) && (g->N % 4 == 0) && (((uintptr_t)g->out32) & 15) == 0 &&
+                            (!g->residual || g->residual != g->out32) && (!g->bias || (((uintptr_t)g->bias) & 15) == 0) &&
+                            (!g->residual || (((uintptr_t)g->residual) & 15) == 0);
+    if (g->a.nb0 * g->a.nb1 != 1 || !linear_epi || ctas * 2 > 148 || total_kb < 8 || !g_split_k) return 1;
+    int s = 148 / ctas;
+    if (s > total_kb / 4) s = total_kb / 4;
+    if (s > 16) s = 16;
+    if (s < 2) return 1;
+    *kb_per_split = (total_kb + s - 1) / s;
+    return (total_kb + *kb_per_split - 1) / *kb_per_split;
+}
 
 int get_encode() {
     if (g_encode) return 0;

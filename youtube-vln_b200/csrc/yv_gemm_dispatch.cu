@@ -9,6 +9,9 @@
 extern "C" int yv_gemm_k32(const YvGemm* g, yv_stream_t stream);
 extern "C" int yv_gemm_k64(const YvGemm* g, yv_stream_t stream);
 extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream);
+extern "C" int yv_gemm_k32_splits(const YvGemm* g);
+extern "C" int yv_gemm_k64_splits(const YvGemm* g);
+extern "C" int yv_gemm_pair_splits(const YvGemm* g, int pair_n);
 
 namespace {
 // 0 = automatic; 32 / 64 = the single-CTA variants; 2 = CTA pairs (tile width chosen per problem);
@@ -37,4 +40,16 @@ extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
     // kernel reaches ~100 % in the main loop with 256-wide tiles but leaves half the SMs idle on the one-wave
     // problems of this step, so it stays opt-in (yv_gemm_set_variant / YVB200_GEMM_VARIANT=2).
     return yv_gemm_k64(g, stream);
+}
+
+// How many K splits yv_gemm would use for this problem (1 = none).  A split launch reduces partial sums into a
+// zero-filled f32 output; a caller that zero-fills the output itself, off its critical path, sets g->out32_zeroed and
+// saves the memset node in front of the kernel.
+extern "C" int yv_gemm_splits(const YvGemm* g) {
+    if (g == nullptr || g->M <= 0 || g->N <= 0 || g->K <= 0) return 1;
+    const int force = g_variant;
+    if (force == 32) return yv_gemm_k32_splits(g);
+    if (force == 2) return yv_gemm_pair_splits(g, 0);
+    if (force == 128 || force == 256) return yv_gemm_pair_splits(g, force);
+    return yv_gemm_k64_splits(g);
 }

@@ -268,11 +268,25 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
-const bool g_split_k = []() { const char* e = getenv("YVB200_SPLIT_K"); return !(e && e[0] == '0'); }();
-
 }  // namespace
 
 void yv_count_launch();
+
+static int pair_width(const YvGemm* g, int pair_n) {
+    if (pair_n != 0) return pair_n;
+    // 256-wide pair tiles halve the operand bytes per FLOP but also halve the CTA count: take them only when
+    // the 128-wide tiling would need more than one resident wave
+    const long long batch = g->a.nb0 * g->a.nb1;
+    const long long ctas128 = 2LL * ((g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((g->N + 127) / 128) * batch;
+    return ctas128 > 2 * 148 ? 256 : 128;
+}
+
+extern "C" int yv_gemm_pair_splits(const YvGemm* g, int pair_n) {
+    pair_n = pair_width(g, pair_n);
+    const int pairs = ((g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((g->N + pair_n - 1) / pair_n);
+    int kbps;
+    return plan_split_k(g, 2 * pairs, (g->K + BLOCK_K - 1) / BLOCK_K, &kbps);
+}
 
 // pair_n: 128 or 256 (0 = choose).  Un-batched and batched problems alike; M is tiled in 256-row pair tiles.
 extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
@@ -292,12 +306,7 @@ extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
     YV_CHECK(a.nb0 == b.nb0 && a.nb1 == b.nb1, "yv_gemm: batch counts differ");
     const long long batch = a.nb0 * a.nb1;
     const int tiles_mp = (g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-    if (pair_n == 0) {
-        // 256-wide pair tiles halve the operand bytes per FLOP but also halve the CTA count: take them only when
-        // the 128-wide tiling would need more than one resident wave (2 CTAs per SM)
-        const long long ctas128 = 2LL * tiles_mp * ((g->N + 127) / 128) * batch;
-        pair_n = ctas128 > 2 * 148 ? 256 : 128;
-    }
+    pair_n = pair_width(g, pair_n);
     CUtensorMap ma, mb;
     if (make_map(&ma, a, g->passes, "A", BLOCK_K, BLOCK_M)) return 1;
     if (make_map(&mb, b, g->passes, "B", BLOCK_K, pair_n / 2)) return 1;
@@ -325,22 +334,7 @@ extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
 
     const int pairs = tiles_mp * ((g->N + pair_n - 1) / pair_n);
     const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
-    p.splits = 1;
-    p.kb_per_split = total_kb;
-    // split-K as in yv_gemm.cu: few tiles, linear epilogue into a plain f32 output (zero-filled by a memset node)
-    const bool linear_epi = g->act == YV_ACT_NONE && !g->aux_out && !g->out_planes && g->out32 &&
-                            (g->ld_out % 4 == 0) && (g->N % 4 == 0) && (((uintptr_t)g->out32) & 15) == 0 &&
-                            (!g->residual || g->residual != g->out32) && (!g->bias || (((uintptr_t)g->bias) & 15) == 0) &&
-                            (!g->residual || (((uintptr_t)g->residual) & 15) == 0);
-    if (batch == 1 && linear_epi && pairs * 4 <= 148 && total_kb >= 8 && g_split_k) {
-        int s = 148 / (2 * pairs);
-        if (s > total_kb / 4) s = total_kb / 4;
-        if (s > 16) s = 16;
-        if (s >= 2) {
-            p.kb_per_split = (total_kb + s - 1) / s;
-            p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-        }
-    }
+    p.splits = plan_split_k(g, 2 * pairs, total_kb, &p.kb_per_split);
     const long long total_pairs = (long long)pairs * batch * p.splits;
     YV_CHECK(2 * total_pairs < 2147483647LL, "yv_gemm: too many tiles");
     p.total_tiles = (int)total_pairs;
@@ -353,7 +347,7 @@ extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
     p.stages = stages;
     dim3 grid((unsigned)(2 * total_pairs), 1, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p.splits > 1)
+    if (p.splits > 1 && !g->out32_zeroed)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
     static bool attr_set = false;
     if (!attr_set) {

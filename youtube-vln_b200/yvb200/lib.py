@@ -19,7 +19,7 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_MUL_GELU_GRAD, ACT_MUL_RELU_MASK = 0, 1, 2, 3,
 
 #: every symbol include/yvb200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
-    "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_set_variant", "yv_split_planes", "yv_split_multi",
+    "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_split_planes", "yv_split_multi",
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
@@ -41,7 +41,8 @@ class YvGemm(C.Structure):
                 ("ld_out", C.c_int64), ("out_sb0", C.c_int64), ("out_sb1", C.c_int64),
                 ("out_planes", C.c_void_p),
                 ("ld_pl", C.c_int64), ("pl_sb0", C.c_int64), ("pl_sb1", C.c_int64), ("pl_plane_stride", C.c_int64),
-                ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("rng", C.c_void_p)]
+                ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("rng", C.c_void_p),
+                ("out32_zeroed", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class YvSplitSeg(C.Structure):
@@ -76,7 +77,7 @@ def load():
 #: bench.py's roofline leg: when True every entry point except yv_gemm returns without launching, so that a captured
 #: step contains the GEMM launches only (their operands are then uninitialised memory: timing only, never results)
 ONLY_GEMM = False
-_ALWAYS = {"yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_set_variant", "yv_rng_advance"}
+_ALWAYS = {"yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_rng_advance"}
 
 
 class _LibProxy:
@@ -111,6 +112,7 @@ def launch_count() -> int:
 def set_gemm_variant(variant: int = 0):
     """Tuning / test knob: 0 automatic, 32 / 64 single-CTA kernels, 2 CTA pairs, 128 / 256 CTA pairs of that width."""
     _check(load().yv_gemm_set_variant(C.c_int(variant)), "gemm_set_variant")
+    _GEMM_VARIANT[0] = variant
 
 
 def _check(rc: int, what: str):
@@ -164,7 +166,8 @@ def op_of(p: Planes, mn_major: bool = False) -> YvOperand:
 def gemm(M: int, N: int, K: int, a: YvOperand, b: YvOperand, *, passes: int = 3, alpha: float = 1.0,
          act: int = ACT_NONE, bias=None, aux_out=None, aux_in=None, residual=None, out32=None, ld_out: int = 0,
          out_sb0: int = 0, out_sb1: int = 0, out_planes: Optional[int] = None, ld_pl: int = 0, pl_sb0: int = 0,
-         pl_sb1: int = 0, pl_plane_stride: int = 0, drop_p: float = 0.0, drop_site: int = 0, rng=None):
+         pl_sb1: int = 0, pl_plane_stride: int = 0, drop_p: float = 0.0, drop_site: int = 0, rng=None,
+         out32_zeroed: bool = False):
     """Raw yv_gemm call.  out32/aux/residual/bias are tensors (or None); out_planes is a device address."""
     g = YvGemm()
     g.M, g.N, g.K, g.passes = M, N, K, passes
@@ -175,6 +178,7 @@ def gemm(M: int, N: int, K: int, a: YvOperand, b: YvOperand, *, passes: int = 3,
     g.out_planes = out_planes
     g.ld_pl, g.pl_sb0, g.pl_sb1, g.pl_plane_stride = ld_pl, pl_sb0, pl_sb1, pl_plane_stride
     g.drop_p, g.drop_site, g.rng = drop_p, drop_site, _p(rng)
+    g.out32_zeroed = 1 if out32_zeroed else 0
     if GEMM_TRACE is None:
         _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
     elif ONLY_GEMM:   # bench.py's roofline leg: shapes only (the launches are being captured into a GEMM-only graph)
@@ -186,6 +190,26 @@ def gemm(M: int, N: int, K: int, a: YvOperand, b: YvOperand, *, passes: int = 3,
         _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
         e1.record()
         GEMM_TRACE.append((M, N, K, int(a.nb0 * a.nb1), passes, e0, e1))
+
+
+_SPLIT_CACHE = {}
+_GEMM_VARIANT = [0]
+
+
+def will_split(M: int, N: int, K: int) -> bool:
+    """Would an un-batched yv_gemm with a linear epilogue into a contiguous, aligned fp32 [M, N] output split K?
+    (Such launches reduce into a zero-filled output; callers use this to zero-fill early, off the dependency chain.)"""
+    key = (M, N, K, _GEMM_VARIANT[0])
+    r = _SPLIT_CACHE.get(key)
+    if r is None:
+        g = YvGemm()
+        g.M, g.N, g.K, g.passes = M, N, K, 3
+        g.a = operand(0x1000, K, M, K, M * K)
+        g.b = operand(0x1000, K, N, K, N * K)
+        g.alpha, g.act = 1.0, ACT_NONE
+        g.out32, g.ld_out = 0x1000, N
+        r = _SPLIT_CACHE[key] = int(load().yv_gemm_splits(C.byref(g))) > 1
+    return r
 
 
 def split_planes(src: torch.Tensor, dst: Optional[Planes] = None) -> Planes:

@@ -68,6 +68,7 @@ class Runtime:
         # weight / bias gradients of the encoder layers are not joined back into the dependency chain of the backward
         # pass: they trail on the helper streams and are joined once at the end (YVB200_DEFER_WGRAD=0: join at once)
         self.defer_wgrad = os.environ.get("YVB200_DEFER_WGRAD", "1") != "0"
+        self.early_zero = os.environ.get("YVB200_EARLY_ZERO", "1") != "0"
         self._join_queued = False
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
         self.main_priority = -1 if prio else 0
@@ -324,6 +325,35 @@ def _f32(*shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+class _EarlyOut:
+    """fp32 [M, N] output of a GEMM contracting over K.  If that launch will split K (partial sums are reduced into a
+    zero-filled output) the buffer is zero-filled NOW on a forked stream, i.e. concurrently with whatever the caller
+    issues before the GEMM; ``ready()`` orders the issuing stream after the fill right before the launch.  This takes
+    the memset node that would otherwise sit in front of every split-K kernel off the dependency chain."""
+    __slots__ = ("t", "zeroed", "_z", "_dev")
+
+    def __init__(self, r: "Runtime", M: int, N: int, K: int, device):
+        self.t = _f32(M, N, device=device)
+        self._dev = device
+        self._z = None
+        self.zeroed = r.early_zero and L.will_split(M, N, K)
+        if self.zeroed:
+            if r.concurrent:
+                cur = torch.cuda.current_stream(device)
+                self._z = r.fork(2)
+                self._z.wait_stream(cur)
+                with torch.cuda.stream(self._z):
+                    self.t.zero_()
+            else:
+                self.t.zero_()
+
+    def ready(self) -> bool:
+        if self._z is not None:
+            torch.cuda.current_stream(self._dev).wait_stream(self._z)
+            self._z = None
+        return self.zeroed
+
+
 def _keep_for(side: torch.cuda.Stream, *objs):
     """Tensors consumed (or produced) by work left running on ``side``: the caching allocator must not hand their
     memory to a later allocation of the issuing stream before that work has run."""
@@ -336,14 +366,18 @@ def _keep_for(side: torch.cuda.Stream, *objs):
 
 def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int, N: int, K: int, device,
                 need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None,
-                db: Optional[torch.Tensor] = None, defer: bool = False):
+                db: Optional[torch.Tensor] = None, defer: bool = False, dx_out: Optional["_EarlyOut"] = None):
     """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K].
     ``db`` may arrive precomputed (fused into the kernel that produced ``dp``).  With ``defer`` the weight / bias
     gradient is left running on the helper stream (joined at the end of the backward pass, see Runtime.defer_join)."""
     dx = dW = None
     have_db = db is not None
+    dx_zeroed = False
     if need_dx:
-        dx = _f32(M, K, device=device)
+        if dx_out is not None:
+            dx, dx_zeroed = dx_out.t, dx_out.ready()
+        else:
+            dx = _f32(M, K, device=device)
     if need_dw:
         dW = _f32(N, K, device=device)
         if not have_db:
@@ -358,7 +392,8 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
             L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
             if not have_db:
                 L.colsum_planes(dp, db)
-        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
+        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual,
+               out32_zeroed=dx_zeroed)
         if trailing:
             _keep_for(side, dp, xp, dW, None if have_db else db)
             r.defer_join()
@@ -366,7 +401,8 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
             cur.wait_stream(side)
         return dx, dW, db
     if need_dx:
-        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual)
+        L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual,
+               out32_zeroed=dx_zeroed)
     if need_dw:
         L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
         if not have_db:
@@ -458,13 +494,14 @@ class DenseResLNFn(Function):
         s, stats, gamma = ctx.saved_tensors
         dz2 = _c2d(dz)
         dev = dz.device
+        dx_out = _EarlyOut(r, M, K, N, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, N, device=dev)
         dsp = Planes.empty(M, N, dev)
         acc = torch.zeros(3, N, dtype=torch.float32, device=dev)          # dgamma, dbeta, dbias in one memset
         L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, N, pre_drop_p=spec.drop_p,
                         pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
         dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2],
-                                 db=acc[2], defer=True)
+                                 db=acc[2], defer=True, dx_out=dx_out)
         return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, acc[0], acc[1], None
 
 
@@ -694,15 +731,16 @@ class AttnBlockFn(Function):
         wqkv = r.arena.get((Wq, Wk, Wv))
         wo = r.arena.get((Wo,))
         m2 = _mask2d(mask, pairs, S)
+        s_out = _EarlyOut(r, M, H, H, dev)
         qkv = Planes.empty(M, 3 * H, dev)
         L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wqkv), passes=r.passes, bias=_cat_bias((bq, bk, bv)),
                out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
         cp = Planes.empty(M, H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
         P, Pp = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None)
-        s = _f32(M, H, device=dev)
+        s = s_out.t
         L.gemm(M, H, H, L.op_of(cp), L.op_of(wo), passes=r.passes, bias=bo, residual=x2, out32=s, ld_out=H,
-               drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=r.rng)
+               drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=r.rng, out32_zeroed=s_out.ready())
         z = _f32(M, H, device=dev)
         zp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
@@ -723,6 +761,7 @@ class AttnBlockFn(Function):
         P, s, stats, gamma = ctx.saved_tensors
         M = pairs * S
         dev = dz.device
+        dx_out = _EarlyOut(r, M, K, 3 * H, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, d(out bias)
@@ -748,7 +787,8 @@ class AttnBlockFn(Function):
         else:
             cur.wait_stream(side)
         need_dx = ctx.needs_input_grad[0]
-        dx, dW, db = _linear_bwd(r, dqkv, xp, wqkv, M, 3 * H, K, dev, need_dx, True, dx_residual=ds, defer=True)
+        dx, dW, db = _linear_bwd(r, dqkv, xp, wqkv, M, 3 * H, K, dev, need_dx, True, dx_residual=ds, defer=True,
+                                 dx_out=dx_out)
         if not need_dx:
             dx = None
         return ((dx.view(pairs, S, K) if dx is not None else None), None,
@@ -784,13 +824,14 @@ class FFNFn(Function):
         xp = planes_of(x, x2)
         w1 = r.arena.get((W1,))
         w2 = r.arena.get((W2,))
+        s_out = _EarlyOut(r, M, H, FF, dev)
         pre = _f32(M, FF, device=dev) if any(ctx.needs_input_grad) else None
         hp = Planes.empty(M, FF, dev)
         L.gemm(M, FF, H, L.op_of(xp), L.op_of(w1), passes=r.passes, bias=b1, act=L.ACT_GELU, aux_out=pre, ld_out=FF,
                out_planes=hp.ptr(), ld_pl=hp.ld, pl_plane_stride=hp.plane_stride)
-        s = _f32(M, H, device=dev)
+        s = s_out.t
         L.gemm(M, H, FF, L.op_of(hp), L.op_of(w2), passes=r.passes, bias=b2, residual=x2, out32=s, ld_out=H,
-               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng)
+               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng, out32_zeroed=s_out.ready())
         z = _f32(M, H, device=dev)
         zp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
@@ -809,6 +850,7 @@ class FFNFn(Function):
         xp, w1, w2, hp = ctx.keep
         pre, s, stats, gamma = ctx.saved_tensors
         dev = dz.device
+        dx_out = _EarlyOut(r, M, H, FF, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, db2
@@ -832,8 +874,9 @@ class FFNFn(Function):
             L.colsum_planes(dprep, db1)
         dx = None
         if ctx.needs_input_grad[0]:                                       # dx = d(pre) . W1 + ds (residual branch)
-            dx = _f32(M, H, device=dev)
-            L.gemm(M, H, FF, L.op_of(dprep), L.op_of(w1, True), passes=r.passes, out32=dx, ld_out=H, residual=ds)
+            dx = dx_out.t
+            L.gemm(M, H, FF, L.op_of(dprep), L.op_of(w1, True), passes=r.passes, out32=dx, ld_out=H, residual=ds,
+                   out32_zeroed=dx_out.ready())
         if side is not cur and r.defer_wgrad:
             _keep_for(side, dsp, hp, dW2, dprep, xp, dW1, db1)
             r.defer_join()
@@ -910,6 +953,8 @@ class BiAttentionFn(Function):
         P1, P2 = ctx.saved_tensors
         dev = dc1.device
         Mv, Mt = pairs * V, pairs * T
+        dxv_out = _EarlyOut(r, Mv, Kv, 3 * H, dev) if ctx.needs_input_grad[0] else None
+        dxt_out = _EarlyOut(r, Mt, Kt, 3 * H, dev) if ctx.needs_input_grad[2] else None
         dO1 = L.split_planes(_c2d(dc1))
         dO2 = L.split_planes(_c2d(dc2))
         d1 = Planes.empty(Mv, 3 * H, dev)
@@ -925,8 +970,10 @@ class BiAttentionFn(Function):
             _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
         _attn_bwd(r, dO2, q1, k2, v2, P2, P2p, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2)
         cur.wait_stream(side)
-        dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True, defer=True)
-        dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True, defer=True)
+        dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True, defer=True,
+                                     dx_out=dxv_out)
+        dxt, dW2, db2 = _linear_bwd(r, d2, xtp, w2, Mt, 3 * H, Kt, dev, ctx.needs_input_grad[2], True, defer=True,
+                                     dx_out=dxt_out)
         return ((dxv.view(pairs, V, Kv) if dxv is not None else None), None,
                 (dxt.view(pairs, T, Kt) if dxt is not None else None), None,
                 dW1[:H], db1[:H], dW1[H:2 * H], db1[H:2 * H], dW1[2 * H:], db1[2 * H:],
