@@ -211,3 +211,44 @@ def test_fused_blocks_agree_with_per_module_nodes(monkeypatch):
         if float(g0[n].norm()) < 1e-6 * gmax:
             continue
         assert float((g1[n] - g0[n]).norm() / g0[n].norm()) < 2e-5, n
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_graphed_step_matches_plain_autograd(use_graph):
+    """yvb200.step.GraphedStep (captured step: fused on-device losses, overlapped weight-plane refresh, weight gradients
+    trailing on helper streams, early zero-fill of split-K outputs) against the plain ``model(...)`` +
+    ``losses.step_losses`` + ``backward()`` sequence on the same weights and batch: total loss and every parameter
+    gradient within 1e-4 (split-K reduction order is the only difference), on the first run and on a replay."""
+    _need_gpu()
+    from yvb200 import ops
+    from yvb200.step import GraphedStep
+    wl = "cfg1"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=7)
+    model = build_lily(cfg, args, device="cuda").eval()
+    ops.rt("cuda").set_precision("bf16x3")
+    b = _dev(batch)
+    out = model(*synth.model_inputs(b))
+    ld = losses.step_losses(b, out, args, training=True)
+    tot = losses.total_loss(ld, args)
+    tot.backward()
+    want_loss = float(tot)
+    want = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    del out, ld, tot, model          # (AccumulateGrad nodes of the plain pass must not outlive it: they belong to
+    #                                   the default stream and would invalidate the capture below)
+    model = build_lily(cfg, args, device="cuda").eval()     # same deterministic synthetic weights
+    step = GraphedStep(model, args, batch, use_graph=use_graph, warmup=1)
+    for rep in range(2):
+        step.load(batch)
+        loss = step.run()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - want_loss) < 1e-4 * abs(want_loss), rep
+        got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+        assert set(got) == set(want)
+        gmax = max(float(v.norm()) for v in want.values())
+        for n, w in want.items():
+            if float(w.norm()) < 1e-6 * gmax:
+                continue
+            # (relative to the tensor, plus a floor for one-element gradients that are a cancellation of large terms)
+            assert float((got[n] - w).norm()) < 1e-4 * float(w.norm()) + 1e-6 * gmax, (rep, n)

@@ -22,6 +22,7 @@ import itertools
 import math
 import os
 import types
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -67,7 +68,11 @@ class Runtime:
         # carry work nobody waits for until the end of a block (weight gradients, bias gradients) and fill in behind
         # weight / bias gradients of the encoder layers are not joined back into the dependency chain of the backward
         # pass: they trail on the helper streams and are joined once at the end (YVB200_DEFER_WGRAD=0: join at once)
-        self.defer_wgrad = os.environ.get("YVB200_DEFER_WGRAD", "1") != "0"
+        # Off by default: a consumer that reads gradients DURING backward on its own stream (stock
+        # DistributedDataParallel bucket hooks) would not see the helper streams.  yvb200.step.GraphedStep, whose
+        # GradientExchange joins the helper streams itself, switches it on for its backward pass.
+        self.defer_wgrad = False
+        self.defer_wgrad_allowed = os.environ.get("YVB200_DEFER_WGRAD", "1") != "0"
         self.early_zero = os.environ.get("YVB200_EARLY_ZERO", "1") != "0"
         self._join_queued = False
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
@@ -114,7 +119,7 @@ class Runtime:
         cur = torch.cuda.current_stream(self.device)
         pool = self._helper_pool.get(cur.cuda_stream)
         if pool is None:
-            n = self.helpers_per_stream if self.defer_wgrad else 1
+            n = self.helpers_per_stream
             pool = self._helper_pool[cur.cuda_stream] = [
                 torch.cuda.Stream(device=self.device, priority=self.helper_priority) for _ in range(n)]
             for i, h in enumerate(pool):
@@ -151,7 +156,18 @@ def rt(device) -> Runtime:
 # weight arena: all GEMM weights as bf16 hi/lo planes in a few flat buffers, refreshed in one launch
 # ----------------------------------------------------------------------------------------------------
 class _Entry:
-    __slots__ = ("params", "rows", "cols", "off", "chunk", "versions", "ptrs", "planes")
+    """One GEMM weight (or a row-wise concatenation of several) in the arena.  Parameters are held weakly so that a
+    model that goes away does not stay alive -- and is not re-split every step -- because of its planes."""
+    __slots__ = ("_prefs", "rows", "cols", "off", "chunk", "versions", "ptrs", "planes")
+
+    @property
+    def params(self):
+        ps = tuple(r() for r in self._prefs)
+        return None if any(p is None for p in ps) else ps
+
+    @params.setter
+    def params(self, ps):
+        self._prefs = tuple(weakref.ref(p) for p in ps)
 
 
 class _Chunk:
@@ -189,6 +205,17 @@ class WeightArena:
         c.used = n_al
         return c, 0
 
+    def _drop(self, key, e: _Entry):
+        e.chunk.entries.remove(e)
+        e.chunk.table = None
+        del self.entries[key]
+
+    def prune(self):
+        """Forget the entries whose parameters no longer exist (their arena space is not reused)."""
+        for key, e in list(self.entries.items()):
+            if e.params is None:
+                self._drop(key, e)
+
     @staticmethod
     def _fresh(e: _Entry) -> bool:
         return len(e.versions) == len(e.params) and all(
@@ -202,6 +229,11 @@ class WeightArena:
         """Planes of the row-wise concatenation of ``params`` (each [rows_i, cols], fp32)."""
         key = tuple(id(p) for p in params)
         e = self.entries.get(key)
+        if e is not None:
+            live = e.params
+            if live is None or any(a is not b for a, b in zip(live, params)):   # stale entry of a freed parameter
+                self._drop(key, e)
+                e = None
         if e is None:
             cols = params[0].shape[1]
             if cols % 8:
@@ -249,6 +281,7 @@ class WeightArena:
         chunks after the first (the arena is filled in forward order, so they hold the later layers) are converted on
         a separate stream while the forward pass starts; ``get`` orders each consumer stream after its chunk."""
         force = force or self.always_stale
+        self.prune()
         cur = torch.cuda.current_stream(self.device)
         if overlap and len(self.chunks) > 1:
             if self.refresh_stream is None:

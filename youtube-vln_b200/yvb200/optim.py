@@ -87,6 +87,7 @@ class FusedAdamW(Optimizer):
             if tab is None:
                 arena = ops.rt(dev).arena
                 planes = {}
+                arena.prune()
                 for e in arena.entries.values():          # GEMM weights: where their hi/lo planes live
                     off = 0
                     for q in e.params:

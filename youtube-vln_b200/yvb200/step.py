@@ -155,6 +155,11 @@ class GraphedStep:
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if use_graph and self.refresh:
+            # the first forward may have added weights to the arena: rebuild the segment tables now, a capture
+            # cannot do the host-to-device copy
+            self.rt.arena.refresh_all(force=True)
+            torch.cuda.synchronize(self.device)
         if use_graph:
             self._zero_grads()
             self.graph = torch.cuda.CUDAGraph()
@@ -192,7 +197,13 @@ class GraphedStep:
             tot = tot + self.args.traj_loss_scale * ld["traj"]
         if self.exchange is not None:
             self.exchange.begin()
-        tot.backward()
+        # weight gradients may trail on the helper streams: they are joined at segment ends by the exchange and at the
+        # end of the pass by the runtime's autograd callback
+        self.rt.defer_wgrad = self.rt.defer_wgrad_allowed
+        try:
+            tot.backward()
+        finally:
+            self.rt.defer_wgrad = False
         if self.exchange is not None:
             self.exchange.end()
         self.loss = tot.detach()
