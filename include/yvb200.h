@@ -112,6 +112,19 @@ typedef struct {
 int yv_adamw_multi(const YvAdamSeg* segs_dev, int32_t nseg, int64_t total_blocks, const float* hyper_dev,
                    yv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batch masking on the device -- SURVEY.md 8(f) "next" #3; replaces utils/dataset/common.py:213-270 (randomize_tokens)
+ * and :272-300 (randomize_regions) of the reference's CPU data path.  The uniform draws are inputs (p in [0,1) per
+ * token / region, replacement token ids, optional host-picked action-word positions), so the result is a pure
+ * function of its arguments and bit-exact against the reference.  tokens / features are updated in place.
+ * ---------------------------------------------------------------------------------------------- */
+int yv_mask_tokens(int64_t* tokens, const uint8_t* mask, const float* p, const int64_t* random_tokens,
+                   const uint8_t* forced /* may be NULL */, int64_t mask_id, int64_t* targets, int64_t n,
+                   yv_stream_t stream);
+int yv_mask_regions(float* features /* [rows, F] */, const float* probs /* [rows, C] */, const int64_t* mask,
+                    const float* p, float* targets /* [rows, C] */, int64_t* targets_mask, int64_t rows, int32_t F,
+                    int32_t C, yv_stream_t stream);
+
 /* dropout RNG state {seed, step}: step += 1 (captured once per training step) */
 int yv_rng_advance(uint64_t* rng, yv_stream_t stream);
 

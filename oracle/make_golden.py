@@ -138,6 +138,71 @@ def run_adamw():
     print("adamw golden ->", path)
 
 
+def run_masking():
+    """The reference's own randomize_tokens / randomize_regions (utils/dataset/common.py:213-300) on seeded inputs.
+    The random draws the functions make internally (torch.rand_like, torch.randint_like, np.random.choice) are
+    recorded by replaying the generator state, so that a device implementation fed with the same draws must
+    reproduce the outputs bit for bit."""
+    import importlib
+    import types
+    refload.load_reference()
+    sys.path.insert(0, refload.REFERENCE_ROOT)
+    common = importlib.import_module("utils.dataset.common")
+    sys.path.remove(refload.REFERENCE_ROOT)
+    vocab = {str(i): i for i in range(30521)}
+    vocab["[MASK]"] = 103
+    tokenizer = types.SimpleNamespace(vocab=vocab)
+    out = {"vocab_size": np.array(len(vocab)), "mask_id": np.array(103)}
+    for case, rate in (("plain", 0.0), ("actions", 0.5)):
+        torch.manual_seed(11 if rate == 0.0 else 12)
+        np.random.seed(5)
+        tokens = torch.randint(1000, 30000, (6, 20))
+        tokens[:, 0] = 101
+        tokens[1, 15:] = 0
+        tokens[4, 9:] = 0
+        for (r, c, a) in ((0, 3, 2187), (0, 7, 2830), (2, 5, 2157), (3, 11, 2187), (5, 2, 2830), (5, 18, 2157)):
+            tokens[r, c] = a
+        mask = tokens > 0
+        args = types.SimpleNamespace(mask_action_rate=rate)
+        st, nst = torch.get_rng_state(), np.random.get_state()
+        pr = torch.rand_like(tokens.float())
+        rnd = torch.randint_like(tokens, len(vocab))
+        forced = torch.zeros_like(tokens, dtype=torch.uint8)
+        if rate > 0:
+            xs, ys = [], []
+            for ac in (2187, 2830, 2157):
+                ix = torch.where(tokens == ac)
+                xs.append(ix[0]); ys.append(ix[1])
+            xs, ys = torch.cat(xs), torch.cat(ys)
+            for mi in np.random.choice(range(len(xs)), int(rate * len(xs))):
+                forced[xs[mi], ys[mi]] = 1
+        torch.set_rng_state(st); np.random.set_state(nst)
+        o_tok, o_tgt = common.randomize_tokens(tokens.clone(), mask, tokenizer, args)
+        out.update({f"tok/{case}/tokens": tokens.numpy(), f"tok/{case}/mask": mask.numpy(), f"tok/{case}/p": pr.numpy(),
+                    f"tok/{case}/random": rnd.numpy(), f"tok/{case}/forced": forced.numpy(),
+                    f"tok/{case}/out_tokens": o_tok.numpy(), f"tok/{case}/out_targets": o_tgt.numpy()})
+    torch.manual_seed(21)
+    feats = torch.randn(5, 36, 16)
+    probs = torch.softmax(torch.randn(5, 36, 12), -1)
+    rmask = torch.ones(5, 36, dtype=torch.long)
+    rmask[1, 30:] = 0
+    rmask[3, 18:] = 0
+    st = torch.get_rng_state()
+    pr = torch.rand_like(rmask.float())
+    torch.set_rng_state(st)
+    o_f, o_t, o_m = common.randomize_regions(feats.clone(), probs, rmask)
+    out.update({"reg/features": feats.numpy(), "reg/probs": probs.numpy(), "reg/mask": rmask.numpy(), "reg/p": pr.numpy(),
+                "reg/out_features": o_f.numpy(), "reg/out_targets": o_t.numpy(), "reg/out_targets_mask": o_m.numpy()})
+    path = os.path.join(ROOT, "tests", "golden", "masking.npz")
+    np.savez_compressed(path, **out)
+    print("masking golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")
+
+
 if __name__ == "__main__":
-    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw"]):
-        run_adamw() if wl == "adamw" else run(wl)
+    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw", "masking"]):
+        if wl == "adamw":
+            run_adamw()
+        elif wl == "masking":
+            run_masking()
+        else:
+            run(wl)

@@ -252,3 +252,40 @@ def test_graphed_step_matches_plain_autograd(use_graph):
                 continue
             # (relative to the tensor, plus a floor for one-element gradients that are a cancellation of large terms)
             assert float((got[n] - w).norm()) < 1e-4 * float(w.norm()) + 1e-6 * gmax, (rep, n)
+
+
+@pytest.mark.parametrize("mode", ["in_batch_pairs", "fast_mode"])
+def test_encoder_batch_expansions_on_cuda(mode):
+    """BertEncoder's in_batch_pairs (every text against every image: batch n -> n*n, reference :771-778) and FAST_MODE
+    (one text broadcast over the image batch, :779-782) expansions: CUDA kernels vs the host path of the same modules."""
+    _need_gpu()
+    import vilbert.vilbert as V
+    cfg = dict(synth.MICRO_CONFIG)
+    cfg[mode] = True
+    config = V.BertConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items()})
+    config.args = synth.make_args()
+    torch.manual_seed(0)
+    mc = V.BertModel(config).eval()
+    synth.load_synthetic_weights(mc, seed=2)
+    mg = V.BertModel(config).eval()
+    mg.load_state_dict(mc.state_dict())
+    mg = mg.cuda()
+    g = torch.Generator().manual_seed(9)
+    n, T, Vr = 3, 12, 12
+    nt = 1 if mode == "fast_mode" else n
+    tok = torch.randint(1, cfg["vocab_size"], (nt, T), generator=g)
+    tmask = torch.ones(nt, T, dtype=torch.long)
+    tmask[0, -3:] = 0
+    feat = torch.randn(n, Vr, cfg["v_feature_size"], generator=g)
+    loc = torch.rand(n, Vr, 12, generator=g)
+    loc[..., 11] = (torch.arange(Vr) // 6).float()
+    vmask = torch.ones(n, Vr, dtype=torch.long)
+    vmask[1, -6:] = 0
+    co = torch.zeros(nt, Vr, T)
+    oc = mc(tok, feat, loc, None, tmask, vmask, co)
+    og = mg(tok.cuda(), feat.cuda(), loc.cuda(), None, tmask.cuda(), vmask.cuda(), co.cuda())
+    expect = n * n if mode == "in_batch_pairs" else n
+    assert oc[0].shape[0] == expect and og[0].shape[0] == expect
+    for a, b in zip(oc[:4], og[:4]):
+        assert a.shape == b.shape
+        assert float((a - b.cpu()).norm() / a.norm()) < TOL

@@ -946,6 +946,61 @@ kl_grad_kernel(const float* __restrict__ logits, long long ld, const float* __re
 }
 
 inline cudaStream_t S(yv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+// ------------------------------------------------------------------------------------------------
+// batch masking (SURVEY 8f "next" #3): BERT token masking and ViLBERT region masking on the device.  The uniform draws
+// are inputs, so the kernels are deterministic integer / byte work (bit-exact against the reference's CPU functions).
+// Thresholds as the reference computes them: Python doubles, cast to float32 by the comparison with a float tensor.
+// ------------------------------------------------------------------------------------------------
+__device__ __constant__ float kMaskThresh[5] = {(float)0.85, (float)(0.85 + 0.15 * 0.8), (float)(0.85 + 0.15 * 0.9),
+                                                (float)(0.85 + 0.15 * 0.1), (float)(0.85 * 0.9)};
+
+__global__ void mask_tokens_kernel(long long* __restrict__ tokens, const unsigned char* __restrict__ mask,
+                                   const float* __restrict__ p, const long long* __restrict__ random,
+                                   const unsigned char* __restrict__ forced, long long mask_id,
+                                   long long* __restrict__ targets, long long n) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float pe = p[i] * (mask[i] ? 1.f : 0.f);
+        long long t = tokens[i], tg = -1;
+        if (forced != nullptr && forced[i]) {        // an action word picked by the host: always [MASK]
+            tg = t;
+            t = mask_id;
+            pe = kMaskThresh[4];
+        }
+        if (pe >= kMaskThresh[0]) {                  // supervised position: 80 % [MASK] ...
+            tg = t;
+            t = mask_id;
+        }
+        if (pe >= kMaskThresh[1]) t = random[i];     // ... 10 % random word ...
+        if (pe >= kMaskThresh[2]) t = tg;            // ... 10 % unchanged
+        tokens[i] = t;
+        targets[i] = tg;
+    }
+}
+
+// one block per region: targets = probs (supervised) or uniform, 90 % of the supervised regions get zero features
+__global__ void __launch_bounds__(256)
+mask_regions_kernel(float* __restrict__ features, const float* __restrict__ probs, const long long* __restrict__ mask,
+                    const float* __restrict__ p, float* __restrict__ targets, long long* __restrict__ targets_mask,
+                    long long rows, int F, int Cc) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const long long r = blockIdx.x;
+    if (r >= rows) return;
+    const float pe = p[r] * (float)mask[r];
+    const bool sup = pe >= kMaskThresh[0];
+    const float uni = 1.0f / (float)Cc;
+    const float* pr = probs + r * Cc;
+    float* tr = targets + r * Cc;
+    for (int c = threadIdx.x; c < Cc; c += blockDim.x) tr[c] = sup ? pr[c] : uni;
+    if (threadIdx.x == 0) targets_mask[r] = sup ? 1 : 0;
+    if (pe >= kMaskThresh[3]) {
+        float* fr = features + r * (long long)F;
+        for (int c = threadIdx.x; c < F; c += blockDim.x) fr[c] = 0.f;
+    }
+}
+
 // YVB200_LN=block selects the older block-per-4-rows LayerNorm kernels (kept for A/B timing)
 const bool g_ln_warp = []() { const char* e = getenv("YVB200_LN"); return !(e && e[0] == 'b'); }();
 
@@ -1187,5 +1242,25 @@ extern "C" int yv_kl_grad(const float* logits, int64_t ld, const float* target, 
     YV_CUDA(yv_launch(kl_grad_kernel, dim3((unsigned)rows), dim3(THREADS), 0, S(stream), logits, ld, target, ld_t, reinterpret_cast<const long long*>(mask),
                                                              cols, count, gscale, dl32, reinterpret_cast<__nv_bfloat16*>(dl_planes),
                                                              ld_p, plane_stride));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_mask_tokens(int64_t* tokens, const uint8_t* mask, const float* p, const int64_t* random_tokens,
+                              const uint8_t* forced, int64_t mask_id, int64_t* targets, int64_t n, yv_stream_t stream) {
+    YV_CHECK(tokens && mask && p && random_tokens && targets && n > 0, "yv_mask_tokens: bad arguments");
+    YV_CUDA(yv_launch(mask_tokens_kernel, dim3(grid_for(n, 256)), dim3(256), 0, S(stream),
+                      reinterpret_cast<long long*>(tokens), mask, p, reinterpret_cast<const long long*>(random_tokens), forced,
+                      (long long)mask_id, reinterpret_cast<long long*>(targets), (long long)n));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_mask_regions(float* features, const float* probs, const int64_t* mask, const float* p, float* targets,
+                               int64_t* targets_mask, int64_t rows, int32_t F, int32_t Cc, yv_stream_t stream) {
+    YV_CHECK(features && probs && mask && p && targets && targets_mask && rows > 0 && F > 0 && Cc > 0,
+             "yv_mask_regions: bad arguments");
+    YV_CHECK(rows < 2147483647LL, "yv_mask_regions: too many regions");
+    YV_CUDA(yv_launch(mask_regions_kernel, dim3((unsigned)rows), dim3(256), 0, S(stream), features, probs,
+                      reinterpret_cast<const long long*>(mask), p, targets, reinterpret_cast<long long*>(targets_mask),
+                      (long long)rows, (int)F, (int)Cc));
     YV_LAUNCHED();
 }

@@ -23,6 +23,7 @@ SYMBOLS = [
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
+    "yv_mask_tokens", "yv_mask_regions",
 ]
 
 
@@ -343,3 +344,16 @@ def kl_grad(logits, ld, target, ld_t, mask, rows, cols, count, gscale, dl32, dl_
                              C.c_void_p(dl_planes.ptr() if dl_planes is not None else None),
                              C.c_int64(dl_planes.ld if dl_planes is not None else 0),
                              C.c_int64(dl_planes.plane_stride if dl_planes is not None else 0), _stream()), "kl_grad")
+
+
+def mask_tokens(tokens, mask_u8, p, random_tokens, forced_u8, mask_id: int, targets):
+    _check(load().yv_mask_tokens(C.c_void_p(tokens.data_ptr()), C.c_void_p(mask_u8.data_ptr()), C.c_void_p(p.data_ptr()),
+                                 C.c_void_p(random_tokens.data_ptr()), C.c_void_p(_p(forced_u8)), C.c_int64(mask_id),
+                                 C.c_void_p(targets.data_ptr()), C.c_int64(tokens.numel()), _stream()), "mask_tokens")
+
+
+def mask_regions(features, probs, mask, p, targets, targets_mask, rows: int, F: int, Cc: int):
+    _check(load().yv_mask_regions(C.c_void_p(features.data_ptr()), C.c_void_p(probs.data_ptr()), C.c_void_p(mask.data_ptr()),
+                                  C.c_void_p(p.data_ptr()), C.c_void_p(targets.data_ptr()),
+                                  C.c_void_p(targets_mask.data_ptr()), C.c_int64(rows), C.c_int32(F), C.c_int32(Cc),
+                                  _stream()), "mask_regions")
