@@ -289,3 +289,39 @@ def test_encoder_batch_expansions_on_cuda(mode):
     for a, b in zip(oc[:4], og[:4]):
         assert a.shape == b.shape
         assert float((a - b.cpu()).norm() / a.norm()) < TOL
+
+
+def test_graphed_step_prefetch_pipeline():
+    """``load`` of the next batch overlaps the step in flight (the copy waits only for the events recorded after the
+    last read of the static inputs).  A, B, A, B issued back to back without host synchronisation must give the losses
+    and gradients of the same batches run one at a time."""
+    _need_gpu()
+    from yvb200 import ops
+    from yvb200.step import GraphedStep
+    wl = "cfg1"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    A = [t.pin_memory() if torch.is_tensor(t) else t for t in synth.make_batch(wl, seed=7)]
+    B = [t.pin_memory() if torch.is_tensor(t) else t for t in synth.make_batch(wl, seed=8)]
+    model = build_lily(cfg, args, device="cuda").eval()
+    ops.rt("cuda").set_precision("bf16x3")
+    step = GraphedStep(model, args, A, use_graph=True)
+    ref = {}
+    for name, bt in (("A", A), ("B", B)):
+        step.load(bt)
+        torch.cuda.synchronize()
+        loss = step.run()
+        torch.cuda.synchronize()
+        ref[name] = (float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert abs(ref["A"][0] - ref["B"][0]) > 1e-4 * abs(ref["A"][0])          # the batches really differ
+    got = []
+    for name in ("A", "B", "A", "B", "B", "A"):
+        step.load(A if name == "A" else B)
+        got.append((name, step.run().clone()))
+    torch.cuda.synchronize()
+    for name, loss in got:
+        assert abs(float(loss) - ref[name][0]) < 1e-5 * abs(ref[name][0]), name
+    gmax = max(float(v.norm()) for v in ref["A"][1].values())
+    for n, p in model.named_parameters():
+        if p.grad is not None and float(ref["A"][1][n].norm()) > 1e-6 * gmax:
+            assert float((p.grad - ref["A"][1][n]).norm()) < 1e-4 * float(ref["A"][1][n].norm()) + 1e-6 * gmax, n

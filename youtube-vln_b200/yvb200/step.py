@@ -125,10 +125,40 @@ class GradientExchange:
             h.remove()
 
 
+class _Consumed(torch.autograd.Function):
+    """Identity whose backward records an (external) CUDA event: placed on the logits that enter the two big losses,
+    it fires right after the loss-gradient kernels have read the target tensors of the batch -- the last reads of the
+    step's static input buffers.  ``GraphedStep.load`` lets the next batch's host-to-device copy wait for these events
+    instead of for the end of the step."""
+
+    @staticmethod
+    def forward(ctx, x, owner):
+        ctx.owner = owner
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ev = torch.cuda.Event(external=True)
+        ev.record(torch.cuda.current_stream(g.device))
+        ctx.owner._consumed.append(ev)
+        return g, None
+
+
 class GraphedStep:
+    #: static inputs read in place by the step (everything else is small and cloned into step-private memory first):
+    #: image_features (read once by the plane split at the start of forward) and image_targets (read by the KL loss
+    #: and its gradient kernel at the start of backward)
+    BIG_INPUTS = (1, 4)
+
     def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
-                 refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None):
+                 refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None,
+                 prefetch: bool = True):
         self.model, self.args = model, args
+        self.prefetch = prefetch
+        self._consumed: List[torch.cuda.Event] = []
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._loaded: Optional[torch.cuda.Event] = None
+        self._launched = False
         self.exchange = exchange
         # NCCL collectives inside the captured graph overlap the exchange with backward; opt-in because a capture
         # with live communicator threads needs thread-local capture mode (YVB200_CAPTURE_NCCL=1).  Default: the
@@ -138,6 +168,7 @@ class GraphedStep:
         if exchange is not None and not self.capture_exchange:
             exchange.defer = True
         self.device = next(model.parameters()).device
+        self.prefetch = self.prefetch and self.device.type == "cuda"
         self.rt = ops.rt(self.device)
         self.refresh = refresh_weights_each_step
         self.static = [t.to(self.device).clone() if torch.is_tensor(t) else t for t in example_batch]
@@ -183,11 +214,28 @@ class GraphedStep:
             # chunk 0 (first layers) on this stream, the rest overlapped with the start of the forward pass
             self.rt.arena.refresh_all(force=True, overlap=self.rt.concurrent)
         b = self.static
+        if self.prefetch:
+            # the next batch may be copied into the static buffers while this step is still running (see ``load``):
+            # small inputs (token ids, locations, masks, targets: some are read again at the very end of backward) are
+            # cloned into step-private memory, the two big ones are read in place and guarded by ``_consumed`` events
+            self._consumed = []
+            b = [t.clone() if (torch.is_tensor(t) and i not in self.BIG_INPUTS) else t for i, t in enumerate(b)]
         co = b[11]
         inputs = (b[6].flatten(0, 1), b[1].flatten(0, 1), b[2].flatten(0, 1), b[10].flatten(0, 1), b[7].flatten(0, 1),
                   b[3].flatten(0, 1), co.reshape(-1, co.size(2), co.size(3)), b[9].flatten(0, 1), b[15])
         out = self.model(*inputs)
         self.rt.arena.join()
+        if self.prefetch:
+            out = dict(out)
+            marked = False
+            for k in ("vision", "language"):
+                if k in out and out[k].requires_grad:
+                    out[k] = _Consumed.apply(out[k], self)
+                    marked = True
+            if not marked or "vision" not in out:       # image_targets unused: the inputs are free after forward
+                ev = torch.cuda.Event(external=True)
+                ev.record(torch.cuda.current_stream(self.device))
+                self._consumed.append(ev)
         ld = fused.step_losses(b, out, self.args, training=True, flat=True)
         tot = 0.0
         for k in ("vision", "language", "ranking"):
@@ -209,16 +257,39 @@ class GraphedStep:
         self.loss = tot.detach()
 
     def load(self, batch: List[torch.Tensor]):
-        """Copy a (pinned host or device) batch into the static buffers (async on the current stream)."""
-        for dst, src in zip(self.static, batch):
-            if torch.is_tensor(dst):
-                dst.copy_(src, non_blocking=True)
+        """Copy a (pinned host or device) batch into the static buffers.  With ``prefetch`` the copy runs on its own
+        stream as soon as the step in flight has finished reading its inputs (start of its backward pass), i.e.
+        overlapped with the rest of that step; the next ``run`` waits for the copy."""
+        if not (self.prefetch and self.device.type == "cuda"):
+            for dst, src in zip(self.static, batch):
+                if torch.is_tensor(dst):
+                    dst.copy_(src, non_blocking=True)
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        cur = torch.cuda.current_stream(self.device)
+        if self._launched and self._consumed:
+            for ev in self._consumed:
+                cs.wait_event(ev)
+        else:
+            cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self.static, batch):
+                if torch.is_tensor(dst):
+                    dst.copy_(src, non_blocking=True)
+            self._loaded = torch.cuda.Event()
+            self._loaded.record(cs)
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.static if torch.is_tensor(t))
 
     def run(self) -> torch.Tensor:
         """One step on the data currently in the static buffers; returns the (device) total loss."""
+        if self._loaded is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._loaded)
+            self._loaded = None
+        self._launched = True
         if self.graph is not None:
             self.graph.replay()
         else:
