@@ -63,23 +63,25 @@ class GradientExchange:
     def _close_segment(self, with_event: bool):
         if not self.pending:
             return
-        ev = None
+        evs = None
         if with_event and self.cuda:
+            # the gradients of this segment were produced on the issuing stream and on the runtime's helper / fork /
+            # branch streams (trailing weight gradients): one external event per stream, recorded where each stream
+            # stands now; nothing is joined into the dependency chain of the backward pass
             from . import ops
             r = ops.rt(self.device)
             cur = torch.cuda.current_stream(self.device)
             capturing = torch.cuda.is_current_stream_capturing()
-            for s_ in [r.branch_stream] + list(r._helpers.values()):
-                if s_ == cur:
-                    continue
-                if capturing:                                 # only streams that belong to this capture can be joined
+            evs = []
+            for s_ in [cur, r.branch_stream] + list(r._helpers.values()):
+                if s_ != cur and capturing:                   # only streams that belong to this capture
                     with torch.cuda.stream(s_):
                         if not torch.cuda.is_current_stream_capturing():
                             continue
-                cur.wait_stream(s_)                           # everything issued so far precedes the event
-            ev = torch.cuda.Event(external=True)
-            ev.record(cur)
-        self.segments.append((ev, self.pending))
+                ev = torch.cuda.Event(external=True)
+                ev.record(s_)
+                evs.append(ev)
+        self.segments.append((evs, self.pending))
         self.pending, self.pending_bytes = [], 0
 
     def end(self):
@@ -91,9 +93,10 @@ class GradientExchange:
     def exchange(self):
         if self.cuda:
             main = torch.cuda.current_stream(self.device)
-            for ev, grads in self.segments:
-                if ev is not None:
-                    self.comm.wait_event(ev)
+            for evs, grads in self.segments:
+                if evs is not None:
+                    for ev in evs:
+                        self.comm.wait_event(ev)
                 else:
                     self.comm.wait_stream(main)
                 with torch.cuda.stream(self.comm):
