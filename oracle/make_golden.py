@@ -198,10 +198,55 @@ def run_masking():
     print("masking golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")
 
 
+def run_featstore():
+    """The reference's own YTbFeaturesReader.__getitem__ (utils/dataset/features_reader.py:153-182) on synthetic
+    records in both key conventions (raw float32 blobs / base64 strings).  The LMDB layer is replaced by a dict: the
+    base class lookup is patched to return the unpickled records, everything above it is the reference's code."""
+    import base64
+    import importlib
+    import pickle
+    refload.load_reference()
+    sys.path.insert(0, refload.REFERENCE_ROOT)
+    fr = importlib.import_module("utils.dataset.features_reader")
+    sys.path.remove(refload.REFERENCE_ROOT)
+    rng = np.random.RandomState(7)
+    store = {}
+    for i, (key, k, old) in enumerate((("vidA/000012", 3, True), ("vidA/000030", 2, False), ("vidB/000001", 4, False),
+                                       ("vidB/000077", 1, True))):
+        w, h = 640 + 16 * i, 360 + 8 * i
+        feats = rng.randn(k, 2048).astype(np.float32)
+        x1 = rng.uniform(0, w / 2, k); y1 = rng.uniform(0, h / 2, k)
+        boxes = np.stack([x1, y1, x1 + rng.uniform(8, w / 2, k), y1 + rng.uniform(8, h / 2, k)], 1).astype(np.float32)
+        probs = rng.dirichlet(np.ones(1601) * 0.1, k).astype(np.float32)
+        if old:
+            item = {"image_width": w, "image_height": h, "feature": feats.tobytes(), "bbox": boxes.tobytes(),
+                    "cls_prob": probs.tobytes()}
+        else:
+            item = {"image_w": str(w), "image_h": str(h), "features": base64.b64encode(feats.tobytes()),
+                    "boxes": base64.b64encode(boxes.tobytes()), "cls_prob": base64.b64encode(probs.tobytes())}
+        store[key] = pickle.dumps(item)
+    reader = object.__new__(fr.YTbFeaturesReader)
+    reader.keys = {k: 0 for k in store}
+    fr.FeaturesReader.__getitem__ = lambda self, keys: [pickle.loads(store[k]) for k in keys]
+    out = {"keys": np.array(list(store)), "records": np.array([np.frombuffer(v, dtype=np.uint8) for v in store.values()],
+                                                                dtype=object)}
+    queries = {"q0": ("vidA/000012", "vidA/000030", "vidB/000001"), "q1": ("vidB/000077",),
+               "q2": ("vidB/000001", "vidA/000012", "vidB/000001", "vidB/000077")}
+    for name, q in queries.items():
+        f, l, p = reader[q]
+        out[f"{name}/query"] = np.array(q)
+        out[f"{name}/features"], out[f"{name}/locations"], out[f"{name}/probs"] = f, l, p
+    path = os.path.join(ROOT, "tests", "golden", "featstore.npz")
+    np.savez_compressed(path, **out)
+    print("featstore golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")
+
+
 if __name__ == "__main__":
-    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw", "masking"]):
+    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw", "masking", "featstore"]):
         if wl == "adamw":
             run_adamw()
+        elif wl == "featstore":
+            run_featstore()
         elif wl == "masking":
             run_masking()
         else:

@@ -325,3 +325,41 @@ def test_graphed_step_prefetch_pipeline():
     for n, p in model.named_parameters():
         if p.grad is not None and float(ref["A"][1][n].norm()) > 1e-6 * gmax:
             assert float((p.grad - ref["A"][1][n]).norm()) < 1e-4 * float(ref["A"][1][n].norm()) + 1e-6 * gmax, n
+
+
+def test_degenerate_masks_match_oracle():
+    """Edge cases of the additive -10000 masks (reference vilbert/vilbert.py:1268-1287): a pair whose instruction is all
+    padding except [CLS], a pair whose trajectory is entirely padded (softmax over all-masked keys is uniform, not NaN),
+    and a pair with nothing masked -- outputs, losses and gradients against the host oracle at 1e-3."""
+    _need_gpu()
+    import vilbert_oracle as O
+    from yvb200 import ops
+    wl = "micro"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    sd = synth.lily_state_dict(cfg, seed=0)
+    batch = [t.clone() if torch.is_tensor(t) else t for t in synth.make_batch(wl, seed=11)]
+    batch[7][0, 0, 1:] = 0                     # instr_mask: only [CLS] left
+    batch[6][0, 0, 1:] = 0
+    batch[3][0, 1, :] = 0                      # image_mask: whole trajectory padded
+    batch[5][0, 1, :] = 0                      # ... so no region of it is supervised
+    batch[7][1, 0, :] = 1                      # nothing masked
+    batch[3][1, 0, :] = 1
+    o_out, o_ld, o_tot, o_grads = O.oracle_step(sd, cfg, args, batch, dtype=torch.float32)
+    model = build_lily(cfg, args, device="cuda").eval()
+    ops.rt("cuda").set_precision("bf16x3")
+    b = _dev(batch)
+    out = model(*synth.model_inputs(b))
+    ld = losses.step_losses(b, out, args, training=True)
+    losses.total_loss(ld, args).backward()
+    for k in o_out:
+        a, r = out[k].detach().cpu().double(), o_out[k].double()
+        assert torch.isfinite(a).all(), k
+        assert float((a - r).norm() / r.norm()) < TOL, k
+    for k in o_ld:
+        assert abs(float(ld[k]) - float(o_ld[k])) < TOL * max(1.0, abs(float(o_ld[k]))), k
+    gmax = max(float(v.norm()) for v in o_grads.values())
+    for n, p in model.named_parameters():
+        if p.grad is None or float(o_grads[n].norm()) < 1e-6 * gmax:
+            continue
+        assert float((p.grad.cpu().double() - o_grads[n].double()).norm() / o_grads[n].double().norm()) < TOL, n
