@@ -70,7 +70,7 @@ def run(workload: str):
     out = {"total_loss": np.float64(float(total.detach())), "ref_seconds": np.float64(dt)}
     for k, v in loss_vals.items():
         out["loss/" + k] = np.float64(v)
-    full = workload == "micro"
+    full = workload == "micro"        # (micro_pad is stored sampled: it pins the padding / degenerate-mask paths)
     for k, v in outputs.items():
         a = v.detach().float().numpy()
         if full or a.size <= N_SAMPLE_OUT:

@@ -113,7 +113,9 @@ def connection_layer(v, v_mask, t, t_mask, sd, p, n_heads):
 
 def text_embeddings(tokens, segs, sd, p="bert.embeddings"):
     pos = torch.arange(tokens.shape[1], device=tokens.device)
-    e = sd[p + ".word_embeddings.weight"][tokens] + sd[p + ".position_embeddings.weight"][pos][None] \
+    # nn.Embedding(..., padding_idx=0) in the reference (vilbert/vilbert.py:225-227): token 0 receives no gradient
+    e = F.embedding(tokens, sd[p + ".word_embeddings.weight"], padding_idx=0) \
+        + sd[p + ".position_embeddings.weight"][pos][None] \
         + sd[p + ".token_type_embeddings.weight"][segs]
     return layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"])
 

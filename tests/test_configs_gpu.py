@@ -334,17 +334,11 @@ def test_degenerate_masks_match_oracle():
     _need_gpu()
     import vilbert_oracle as O
     from yvb200 import ops
-    wl = "micro"
-    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    wl = "micro_pad"                            # synth applies the degenerate masks; the oracle is pinned on this
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]          # workload by tests/golden/micro_pad.npz
     args = synth.workload_args(wl)
     sd = synth.lily_state_dict(cfg, seed=0)
-    batch = [t.clone() if torch.is_tensor(t) else t for t in synth.make_batch(wl, seed=11)]
-    batch[7][0, 0, 1:] = 0                     # instr_mask: only [CLS] left
-    batch[6][0, 0, 1:] = 0
-    batch[3][0, 1, :] = 0                      # image_mask: whole trajectory padded
-    batch[5][0, 1, :] = 0                      # ... so no region of it is supervised
-    batch[7][1, 0, :] = 1                      # nothing masked
-    batch[3][1, 0, :] = 1
+    batch = synth.make_batch(wl, seed=11)
     o_out, o_ld, o_tot, o_grads = O.oracle_step(sd, cfg, args, batch, dtype=torch.float32)
     model = build_lily(cfg, args, device="cuda").eval()
     ops.rt("cuda").set_precision("bf16x3")

@@ -39,7 +39,7 @@ def _run(wl, mode=None, train=False):
             model)
 
 
-@pytest.mark.parametrize("wl", ["micro", "cfg1", "cfg2"])
+@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1", "cfg2"])
 def test_cuda_path_matches_reference_golden(golden_dir, wl):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

@@ -68,7 +68,7 @@ def _check_grads(g, grads, rtol):
     return n
 
 
-@pytest.mark.parametrize("wl", ["micro", "cfg1"])
+@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1"])
 def test_oracle_matches_reference_golden(golden_dir, wl):
     g = _load(golden_dir, wl)
     cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]

@@ -56,6 +56,9 @@ CONFIGS = {"full": FULL_CONFIG, "tiny": TINY_CONFIG, "micro": MICRO_CONFIG}
 #: named workloads: (model config, items bs, candidates C, frames P, regions/frame B, tokens T)
 WORKLOADS = {
     "micro": dict(config="micro", bs=2, cands=4, frames=2, boxes=6, tokens=12),
+    # degenerate masks: an instruction that is all padding (token id 0 = the embedding's padding_idx) except [CLS], a
+    # fully padded trajectory, a pair with nothing masked
+    "micro_pad": dict(config="micro", bs=2, cands=4, frames=2, boxes=6, tokens=12, degenerate=True),
     "cfg1": dict(config="tiny", bs=1, cands=2, frames=1, boxes=36, tokens=20, args=dict(pretrain=False)),
     "cfg2": dict(config="full", bs=2, cands=4, frames=8, boxes=36, tokens=80),
     "cfg3": dict(config="full", bs=4, cands=4, frames=8, boxes=36, tokens=80),
@@ -187,6 +190,13 @@ def make_batch(workload: str, seed: int = 1, rank: int = 0) -> List[torch.Tensor
     batch[11] = co
     batch[12] = torch.zeros(bs, dtype=torch.long)
     batch[13] = opt_mask
+    if WORKLOADS[workload].get("degenerate"):
+        batch[7][0, 0, 1:] = 0                 # instr_mask: only [CLS] left ...
+        batch[6][0, 0, 1:] = 0                 # ... and the tokens are padding (id 0)
+        batch[3][0, 1, :] = 0                  # image_mask: whole trajectory padded ...
+        batch[5][0, 1, :] = 0                  # ... so none of its regions is supervised
+        batch[7][1, 0, :] = 1                  # nothing masked
+        batch[3][1, 0, :] = 1
     batch[14] = torch.zeros(bs, dtype=torch.long)
     batch[15] = torch.zeros(1)
     return batch
