@@ -163,13 +163,7 @@ class GraphedStep:
         self._loaded: Optional[torch.cuda.Event] = None
         self._launched = False
         self.exchange = exchange
-        # NCCL collectives inside the captured graph overlap the exchange with backward; opt-in because a capture
-        # with live communicator threads needs thread-local capture mode (YVB200_CAPTURE_NCCL=1).  Default: the
-        # bucketed exchange runs right after the replay on the communication stream.
-        import os as _os
-        self.capture_exchange = exchange is not None and _os.environ.get("YVB200_CAPTURE_NCCL", "0") == "1"
-        if exchange is not None and not self.capture_exchange:
-            exchange.defer = True
+        # (the exchange's NCCL calls stay outside the graph: inside it only per-segment external events are recorded)
         self.device = next(model.parameters()).device
         self.prefetch = self.prefetch and self.device.type == "cuda"
         self.rt = ops.rt(self.device)
