@@ -292,6 +292,49 @@ def main():
                 "algorithmic_gflop_per_step": g_flop / 1e9, "tensor_pipe_flop_multiplier": hw_mult,
                 "frac_of_tensor_pipe": achieved * hw_mult / peak_tf}
 
+    # the single most expensive launch of the step on its own: the Q|K|V projection of the vision stream in
+    # BertBiAttention / BertImageSelfAttention (2304 x 3072 x 1024 at 8 pairs), timed back to back with CUDA events;
+    # `traffic` is the DRAM read + write of that launch from the committed ncu --set full capture of this round
+    try:
+        Md, Nd, Kd = pairs * wl["frames"] * wl["boxes"], 3 * cfg["bi_hidden_size"], cfg["v_hidden_size"]
+        pa = lib.split_planes(torch.randn(Md, Kd, device=dev))
+        pb = lib.split_planes(torch.randn(Nd, Kd, device=dev) * 0.05)
+        bias_d = torch.randn(Nd, device=dev)
+        outp = lib.Planes.empty(Md, Nd, dev)
+        passes = 3 if a.precision == "bf16x3" else 1
+
+        def one():
+            lib.gemm(Md, Nd, Kd, lib.op_of(pa), lib.op_of(pb), passes=passes, bias=bias_d, out_planes=outp.ptr(),
+                     ld_pl=outp.ld, pl_plane_stride=outp.plane_stride)
+        for _ in range(5):
+            one()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            one()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) / 50 * 1e3
+        tf = 2.0 * Md * Nd * Kd / (us * 1e-6) / 1e12
+        burst = peak_tf
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                burst = float(json.load(fh).get("bf16_tflops", peak_tf))
+        except Exception:
+            pass
+        roofline["dominant_launch"] = {
+            "what": f"yv_gemm {Md}x{Nd}x{Kd} (vision Q|K|V projection), {passes} pass(es), plane output, 50 launches back to back",
+            "us_per_launch": us, "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+            "frac_of_tensor_pipe": tf * hw_mult / burst, "peak_source": "bf16_tflops (burst: kernel timed alone)",
+            "traffic": 22.2e6 if (Md, Nd, Kd, passes) == (2304, 3072, 1024, 3) else None,
+            "traffic_source": "profiles/r1_c_gemm_ncu_full_key_metrics.csv: dram__bytes_read.sum + dram__bytes_write.sum "
+                              "of this launch (operands 22.0 MB once + 0.1 MB written back before the capture ended)",
+            "algorithmic_bytes": 2.0 * 2 * (Md * Kd + Nd * Kd) + 2.0 * 2 * Md * Nd}
+        del pa, pb, outp
+    except Exception as e:  # never let the extra evidence break the bench line
+        roofline["dominant_launch"] = {"error": repr(e)[:200]}
+
     # informational: the same step issued as stock PyTorch fp32 ops on this GPU (the oracle restatement on CUDA
     # tensors, eval-mode dropout, TF32 off) -- what the reference's unfused ATen path costs on a B200
     torch_gpu = None
