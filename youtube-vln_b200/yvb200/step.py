@@ -10,7 +10,7 @@ from typing import List, Optional
 
 import torch
 
-from . import fused, lib, ops, synth
+from . import fused, lib, ops
 
 _FLOAT_FIELDS = (1, 2, 4)          # image_features, image_locations, image_targets
 
