@@ -61,6 +61,8 @@ def run(workload: str):
     total = 0.0
     loss_vals = {}
     for task in ("vision", "language", "ranking", "traj"):
+        if task not in outputs:                 # objective switched off for this workload (ranking-only fine-tune)
+            continue
         _, _, loss, _ = ui.get_loss_correct(tuple(batch), outputs, task, args, None, True)
         loss_vals[task] = float(loss.detach())
         total = total + (args.traj_loss_scale * loss if task == "traj" else loss)

@@ -68,7 +68,7 @@ def _check_grads(g, grads, rtol):
     return n
 
 
-@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1"])
+@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1", "cfg4_p32_n2", "cfg3_rank"])
 def test_oracle_matches_reference_golden(golden_dir, wl):
     g = _load(golden_dir, wl)
     cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
@@ -76,6 +76,7 @@ def test_oracle_matches_reference_golden(golden_dir, wl):
     sd = synth.lily_state_dict(cfg, seed=0)
     batch = synth.make_batch(wl, seed=1)
     outs, ld, tot, grads = O.oracle_step(sd, cfg, args, batch, dtype=torch.float32)
+    assert {f"loss/{k}" for k in ld} == {k for k in g.files if k.startswith("loss/")}
     for k, v in ld.items():
         assert abs(float(v) - float(g[f"loss/{k}"])) <= 2e-5 * max(1.0, abs(float(g[f"loss/{k}"]))), k
     assert abs(float(tot) - float(g["total_loss"])) <= 2e-5 * abs(float(g["total_loss"]))
