@@ -2,12 +2,13 @@
 //
 //   D[z] = epilogue(alpha * sum_p A_p[z] . B_p[z]^T)        p in {(hi,hi)} or {(hi,hi),(hi,lo),(lo,hi)}
 //
-// One CTA per 128x128 output tile, 192 threads:
-//   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d (swizzled) into a 3/6-stage, 96 KB ring
-//              (128x128x32 tiles keep the CTA under half an SM's shared memory: two CTAs co-reside, so one
-//               CTA's prologue / epilogue overlaps the other's MMA main loop)
-//   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), commits to mbarriers
+// One CTA per 128x128 output tile, 320 threads:
+//   warp 0   : TMA producer (one lane) -- cp.async.bulk.tensor.5d (swizzled) into a 3-stage (bf16x3) / 6-stage (bf16)
+//              mbarrier ring: 192 KB in the persistent k64 build (default), 96 KB in the k32 build (two CTAs per SM)
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one lane), commits to mbarriers; two 128-column accumulators in the
+//              persistent build so that the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-9: epilogue -- tcgen05.ld 32x32 chunks, transposed through swizzled smem for coalesced I/O
+//              (yv_gemm_common.cuh: compile-time specialised per activation / dropout / split-K)
 // Operands may be K-major or MN-major (transposed views): dgrad / wgrad / attention products need no
 // explicit transposes.  Out-of-bounds rows/cols/k are zero-filled by TMA (each batch dim is its own
 // tensor-map dim), so ragged shapes (T=80, vocab 30522, 1601 classes) need no padding copies.
