@@ -60,3 +60,23 @@ def assemble(items):
 def read(store: dict, keys):
     """``store``: key -> pickled record bytes (what the LMDB holds)."""
     return assemble([pickle.loads(store[k]) for k in keys])
+
+
+def visual_features(store: dict, steps, max_path_length: int, max_num_boxes: int):
+    """utils/dataset/all_dataset.py:294-345 (+ the float32 / int64 conversion of :236-239): ``steps`` is a list of key
+    tuples (one tuple of frame keys per trajectory step).  float64 staging arrays exactly as the reference."""
+    path_length = min(len(steps), max_path_length)
+    pf, pb, pp, pm = [], [], [], []
+    for i, keys in enumerate(steps):
+        features, boxes, probs = read(store, keys)
+        nb = min(len(boxes), max_num_boxes)
+        f = np.zeros((max_num_boxes, 2048)); f[:nb] = features[:nb]
+        b = np.zeros((max_num_boxes, 12)); b[:nb, :11] = boxes[:nb, :11]; b[:, 11] = np.ones(max_num_boxes) * i
+        p = np.zeros((max_num_boxes, 1601)); p[:nb] = probs[:nb]
+        pf.append(f); pb.append(b); pp.append(p); pm.append([1] * nb + [0] * (max_num_boxes - nb))
+    for idx in range(path_length, max_path_length):
+        b = np.zeros((max_num_boxes, 12)); b[:, 11] = np.ones(max_num_boxes) * idx
+        pf.append(np.zeros((max_num_boxes, 2048))); pb.append(b); pp.append(np.zeros((max_num_boxes, 1601)))
+        pm.append([0] * max_num_boxes)
+    return (np.vstack(pf).astype(np.float32), np.vstack(pb).astype(np.float32), np.vstack(pp).astype(np.float32),
+            np.hstack(pm).astype(np.int64))

@@ -238,6 +238,26 @@ def run_featstore():
         f, l, p = reader[q]
         out[f"{name}/query"] = np.array(q)
         out[f"{name}/features"], out[f"{name}/locations"], out[f"{name}/probs"] = f, l, p
+    # trajectory assembly: the reference's BaseDataset._get_visual_features (utils/dataset/all_dataset.py:294-345) on
+    # top of that reader, then the float32 / int64 conversion of __getitem__ (:236-239)
+    import inspect
+    import types
+    inspect.ArgSpec = getattr(inspect, "ArgSpec", inspect.FullArgSpec)      # removed from Python 3.11 (import-time only)
+    sys.path.insert(0, refload.REFERENCE_ROOT)
+    ds = importlib.import_module("utils.dataset.all_dataset")
+    sys.path.remove(refload.REFERENCE_ROOT)
+    fake = types.SimpleNamespace(args=types.SimpleNamespace(max_path_length=4, max_num_boxes=4), _features_reader=reader,
+                                 get_feature_key=lambda listing, pid: f"{listing}/{pid:06d}")
+    trajectories = {"t0": [("vidA", 12), ("vidB", (1, 77)), ("vidA", 30)], "t1": [("vidB", 77)],
+                    "t2": [("vidA", 30), ("vidA", 12), ("vidB", 1), ("vidB", 77)]}
+    for name, traj in trajectories.items():
+        f, b, p, m = ds.BaseDataset._get_visual_features(fake, traj)
+        out[f"{name}/steps"] = np.array(["|".join(fake.get_feature_key(l, q) for q in ((pid,) if isinstance(pid, int) else pid))
+                                         for l, pid in traj])
+        out[f"{name}/features"] = torch.from_numpy(np.array(f)).float().numpy()
+        out[f"{name}/boxes"] = torch.from_numpy(np.array(b)).float().numpy()
+        out[f"{name}/probs"] = torch.from_numpy(np.array(p)).float().numpy()
+        out[f"{name}/masks"] = torch.from_numpy(np.array(m)).long().numpy()
     path = os.path.join(ROOT, "tests", "golden", "featstore.npz")
     np.savez_compressed(path, **out)
     print("featstore golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")

@@ -69,3 +69,31 @@ def test_shard_layout_and_errors(shard, tmp_path):
     assert _same(f, G["q1/features"])
     with pytest.raises(RuntimeError):
         FS.ShardReader(__file__)
+
+
+TRAJ = ["t0", "t1", "t2"]
+
+
+def _steps(name):
+    return [tuple(str(x).split("|")) for x in G[f"{name}/steps"]]
+
+
+@pytest.mark.parametrize("t", TRAJ)
+def test_oracle_trajectory_matches_reference_dataset(t):
+    f, b, p, m = FO.visual_features(STORE, _steps(t), 4, 4)
+    assert _same(f, G[f"{t}/features"]) and _same(b, G[f"{t}/boxes"]) and _same(p, G[f"{t}/probs"]) and _same(m, G[f"{t}/masks"])
+
+
+@pytest.mark.parametrize("t", TRAJ)
+def test_assemble_path_matches_reference_dataset(shard, t):
+    r = FS.ShardReader(shard)
+    f, b, p, m = FS.assemble_path(r, _steps(t), 4, 4)
+    assert _same(f, G[f"{t}/features"]) and _same(b, G[f"{t}/boxes"]) and _same(p, G[f"{t}/probs"]) and _same(m, G[f"{t}/masks"])
+    # into caller-provided (e.g. pinned) buffers that hold garbage
+    out = (np.full_like(f, 7), np.full_like(b, 7), np.full_like(p, 7), np.full_like(m, 7))
+    FS.assemble_path(r, _steps(t), 4, 4, out=out)
+    assert all(_same(x, y) for x, y in zip(out, (f, b, p, m)))
+    with pytest.raises(TypeError):
+        FS.assemble_path(r, [("missing/1",)], 4, 4)
+    with pytest.raises(ValueError):
+        FS.assemble_path(r, _steps(t), 5, 4, out=out)

@@ -198,3 +198,59 @@ class ShardReader:
         locations[0] = (0, 0, 1, 1, 1, 0, 1, 0, 1, 0, 1)
         probs[0] = np.ones(shape=(1, P_DIM)) / P_DIM
         return features, locations, probs
+
+
+def assemble_path(reader: "ShardReader", steps: Sequence[Sequence[str]], max_path_length: int, max_num_boxes: int,
+                  out=None):
+    """One trajectory as the model wants it -- the reference's ``BaseDataset._get_visual_features``
+    (utils/dataset/all_dataset.py:294-345) followed by the float32 / int64 conversion of ``__getitem__`` (:236-239).
+
+    ``steps[i]`` is the tuple of frame keys of trajectory step i (several keys = several photos of one step: their
+    regions share one global row, features_reader.py:153-182).  Every step is cut / zero-padded to ``max_num_boxes``
+    rows, column 11 of the boxes carries the step index, missing steps up to ``max_path_length`` are all padding.
+    Returns ``(features f32 [S*B, 2048], boxes f32 [S*B, 12], probs f32 [S*B, 1601], masks i64 [S*B])`` with
+    S = max(len(steps), max_path_length) -- bit-identical to the reference, but written once, in float32, straight
+    into ``out`` (e.g. slices of a pinned batch buffer) instead of through per-step float64 staging arrays."""
+    B = int(max_num_boxes)
+    S = max(len(steps), int(max_path_length))
+    if out is None:
+        out = (np.empty((S * B, F_DIM), np.float32), np.empty((S * B, 12), np.float32),
+               np.empty((S * B, P_DIM), np.float32), np.empty((S * B,), np.int64))
+    feats, boxes, probs, masks = out
+    if feats.shape != (S * B, F_DIM) or boxes.shape != (S * B, 12) or probs.shape != (S * B, P_DIM) or masks.shape != (S * B,):
+        raise ValueError("assemble_path: output buffers do not match the trajectory shape")
+    feats[:] = 0
+    boxes[:] = 0
+    probs[:] = 0
+    masks[:] = 0
+    for i in range(S):
+        boxes[i * B:(i + 1) * B, 11] = i
+    for i, keys in enumerate(steps):
+        for key in keys:
+            if not isinstance(key, str) or key not in reader.keys:
+                raise TypeError(f"invalid key: {key}")
+        parts = [reader.rows(k) for k in keys]
+        total = sum(len(f) for f, _, _ in parts)
+        if total == 0:
+            raise RuntimeError("Features could not be correctly read")
+        lo = i * B
+        # row 0 of a step: the global entry (mean feature over ALL regions of the step, unit box, uniform probabilities)
+        if len(parts) == 1:
+            g = parts[0][0].mean(axis=0, keepdims=True)
+        else:
+            g = np.concatenate([f for f, _, _ in parts], axis=0).mean(axis=0, keepdims=True)
+        feats[lo] = g
+        boxes[lo, :11] = (0, 0, 1, 1, 1, 0, 1, 0, 1, 0, 1)
+        probs[lo] = (np.ones(shape=(1, P_DIM)) / P_DIM)
+        n = 1
+        for f, b5, p in parts:
+            take = min(len(f), B - n)
+            if take <= 0:
+                break
+            feats[lo + n:lo + n + take] = f[:take]
+            boxes[lo + n:lo + n + take, 0:5] = b5[:take]
+            boxes[lo + n:lo + n + take, 5:11] = 1
+            probs[lo + n:lo + n + take] = p[:take]
+            n += take
+        masks[lo:lo + min(n, B)] = 1
+    return feats, boxes, probs, masks
