@@ -232,25 +232,50 @@ def test_layernorm_fwd_bwd(L, M, Cd):
     assert _rel(dbias, x.grad.sum(0)) < 1e-4
 
 
-def test_softmax_fwd_bwd(L):
-    pairs, heads, Tq, Tk = 2, 3, 20, 288
+@pytest.mark.parametrize("Tq,Tk", [(20, 288), (80, 80), (7, 36), (5, 12), (3, 1152), (2, 2048), (9, 50), (4, 130)])
+def test_softmax_fwd_bwd(L, Tq, Tk):
+    """Vectorised kernels (Tk % 4 == 0) and the scalar fall-back (Tk = 50, 130), rows padded to 8 floats as in ops.py."""
+    pairs, heads = 2, 3
     rows = pairs * heads * Tq
+    ld = (Tk + 7) // 8 * 8
     S = _mk(rows, Tk, 30, 3.0)
     mask = torch.zeros(pairs, Tk, device="cuda")
-    mask[1, -36:] = -10000.0
+    mask[1, -(Tk // 8 + 1):] = -10000.0
     Sd = S.double().clone().requires_grad_(True)
     ref = torch.softmax(Sd * 0.125 + mask.double().repeat_interleave(heads * Tq, 0), -1)
-    work = S.clone()
-    pp = L.Planes.empty(rows, Tk, "cuda")
-    L.softmax_fwd(work, Tk, mask, rows, Tk, heads * Tq, 0.125, pp)
+    work = torch.full((rows, ld), float("nan"), device="cuda")
+    work[:, :Tk] = S
+    pp = L.Planes.empty(rows, Tk, "cuda", ld=ld)
+    L.softmax_fwd(work, ld, mask, rows, Tk, heads * Tq, 0.125, pp)
     torch.cuda.synchronize()
-    assert _rel(work, ref) < 1e-6 and _rel(pp.float(), ref) < 2e-5
-    dP = _mk(rows, Tk, 31)
-    ref.backward(dP.double())
-    dsp = L.Planes.empty(rows, Tk, "cuda")
-    L.softmax_bwd(work, dP, Tk, rows, Tk, 0.125, dsp)
+    assert _rel(work[:, :Tk], ref) < 1e-6 and _rel(pp.float(), ref) < 2e-5
+    dP = torch.zeros(rows, ld, device="cuda")
+    dP[:, :Tk] = _mk(rows, Tk, 31)
+    ref.backward(dP[:, :Tk].double())
+    dsp = L.Planes.empty(rows, Tk, "cuda", ld=ld)
+    L.softmax_bwd(work, dP, ld, rows, Tk, 0.125, dsp)
     torch.cuda.synchronize()
     assert _rel(dsp.float(), Sd.grad) < 2e-5
+    # dropout: forward and backward draw the same mask (keys row * Tk + column), keep-rate ~ 1 - p
+    rng = torch.tensor([77, 5], dtype=torch.int64, device="cuda")
+    w2 = work.clone()
+    w2[:, :Tk] = S
+    pd = L.Planes.empty(rows, Tk, "cuda", ld=ld)
+    L.softmax_fwd(w2, ld, mask, rows, Tk, heads * Tq, 0.125, pd, 0.25, 9, rng)
+    kept = pd.float() != 0
+    live = ref > 1e-30
+    if int(live.sum()) > 2000:
+        assert abs(float(kept[live].float().mean()) - 0.75) < 0.05
+    assert _rel(pd.float()[kept], (ref / 0.75)[kept]) < 2e-5
+    ones = torch.zeros(rows, ld, device="cuda")
+    ones[:, :Tk] = 1.0
+    dsd = L.Planes.empty(rows, Tk, "cuda", ld=ld)
+    L.softmax_bwd(w2, ones, ld, rows, Tk, 1.0, dsd, 0.25, 9, rng)
+    torch.cuda.synchronize()
+    P = w2[:, :Tk].double()
+    dPm = kept.double() / 0.75                      # what backward must have used as the masked upstream gradient
+    want = P * (dPm - (dPm * P).sum(-1, keepdim=True))
+    assert _rel(dsd.float(), want) < 2e-5
 
 
 def test_embeddings_and_colsum(L):

@@ -600,6 +600,110 @@ softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd, l
     }
 }
 
+// Vectorised variants (cols, leading dimensions and plane stride multiples of 4, 16-byte aligned rows): lane l owns the
+// float4 column groups l, l + 32, ... -- 512-byte warp loads, 8-byte plane stores, a quarter of the memory
+// instructions of the scalar kernels above.  Same dropout keys (row * cols + column) as the scalar kernels.
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+softmax_fwd_vec_kernel(float* __restrict__ s, long long ld_s, const float* __restrict__ mask, long long rows, int cols,
+                       long long rows_per_pair, float scale, __nv_bfloat16* __restrict__ pp, long long ld_p,
+                       long long plane_stride, float drop_p, unsigned drop_site, const unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* sr = s + row * ld_s;
+    const float* mr = mask ? mask + (row / rows_per_pair) * cols : nullptr;
+    float4 v[NV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (c < cols) {
+            const float4 x = *reinterpret_cast<const float4*>(sr + c);
+            const float4 m = mr ? __ldg(reinterpret_cast<const float4*>(mr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] = make_float4(x.x * scale + m.x, x.y * scale + m.y, x.z * scale + m.z, x.w * scale + m.w);
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+    mx = yv_warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if ((lane + 32 * i) * 4 < cols)
+            v[i] = make_float4(expf(v[i].x - mx), expf(v[i].y - mx), expf(v[i].z - mx), expf(v[i].w - mx));
+        else
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    sum = yv_warp_sum(sum);
+    const float inv = 1.f / sum;
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c >= cols) break;
+        float pr[4] = {v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv};
+        *reinterpret_cast<float4*>(sr + c) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+        __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float pd = pr[e];
+            if (drop.thresh) pd *= yv_drop_mul(drop, (uint32_t)(row * cols + c + e));
+            yv_split(pd, h4[e], l4[e]);
+        }
+        *reinterpret_cast<uint2*>(pp + row * ld_p + c) = *reinterpret_cast<uint2*>(h4);
+        *reinterpret_cast<uint2*>(pp + plane_stride + row * ld_p + c) = *reinterpret_cast<uint2*>(l4);
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+softmax_bwd_vec_kernel(const float* __restrict__ p, const float* __restrict__ dpd, long long ld_s, long long rows, int cols,
+                       float scale, __nv_bfloat16* __restrict__ dsp, long long ld_p, long long plane_stride, float drop_p,
+                       unsigned drop_site, const unsigned long long* rng) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* pr = p + row * ld_s;
+    const float* dr = dpd + row * ld_s;
+    const YvDrop drop = yv_drop_make(rng, drop_site, drop_p);
+    float4 pv[NV], dv[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        pv[i] = dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < cols) {
+            pv[i] = *reinterpret_cast<const float4*>(pr + c);
+            dv[i] = *reinterpret_cast<const float4*>(dr + c);
+            if (drop.thresh) {
+                const uint32_t i0 = (uint32_t)(row * cols + c);
+                dv[i].x *= yv_drop_mul(drop, i0); dv[i].y *= yv_drop_mul(drop, i0 + 1);
+                dv[i].z *= yv_drop_mul(drop, i0 + 2); dv[i].w *= yv_drop_mul(drop, i0 + 3);
+            }
+            dot += (dv[i].x * pv[i].x + dv[i].y * pv[i].y) + (dv[i].z * pv[i].z + dv[i].w * pv[i].w);
+        }
+    }
+    dot = yv_warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c >= cols) break;
+        const float ds[4] = {scale * pv[i].x * (dv[i].x - dot), scale * pv[i].y * (dv[i].y - dot),
+                             scale * pv[i].z * (dv[i].z - dot), scale * pv[i].w * (dv[i].w - dot)};
+        __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) yv_split(ds[e], h4[e], l4[e]);
+        *reinterpret_cast<uint2*>(dsp + row * ld_p + c) = *reinterpret_cast<uint2*>(h4);
+        *reinterpret_cast<uint2*>(dsp + plane_stride + row * ld_p + c) = *reinterpret_cast<uint2*>(l4);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // embeddings
 // ------------------------------------------------------------------------------------------------
@@ -1001,6 +1105,8 @@ mask_regions_kernel(float* __restrict__ features, const float* __restrict__ prob
     }
 }
 
+// YVB200_SOFTMAX=scalar selects the scalar softmax kernels for every shape (kept for A/B timing)
+const bool g_softmax_vec = []() { const char* e = getenv("YVB200_SOFTMAX"); return !(e && e[0] == 's'); }();
 // YVB200_LN=block selects the older block-per-4-rows LayerNorm kernels (kept for A/B timing)
 const bool g_ln_warp = []() { const char* e = getenv("YVB200_LN"); return !(e && e[0] == 'b'); }();
 
@@ -1115,6 +1221,19 @@ extern "C" int yv_softmax_fwd(float* s, int64_t ld_s, const float* mask, int64_t
     const dim3 grid((unsigned)((rows + WARPS - 1) / WARPS));
     auto* pp = reinterpret_cast<__nv_bfloat16*>(p_planes);
     auto* rp = reinterpret_cast<const unsigned long long*>(rng);
+    const bool vec = g_softmax_vec && cols % 4 == 0 && ld_s % 4 == 0 && ld_p % 4 == 0 && plane_stride % 4 == 0 &&
+                     (((uintptr_t)s | (uintptr_t)mask) & 15) == 0 && (((uintptr_t)p_planes) & 7) == 0;
+    if (vec) {
+#define YV_SMFV(NV) YV_CUDA(yv_launch(softmax_fwd_vec_kernel<NV>, grid, dim3(THREADS), 0, S(stream), s, ld_s, mask, rows, cols, \
+                                      rows_per_pair, scale, pp, ld_p, plane_stride, drop_p, drop_site, rp))
+        if (cols <= 128) YV_SMFV(1);
+        else if (cols <= 384) YV_SMFV(3);
+        else if (cols <= 640) YV_SMFV(5);
+        else if (cols <= 1152) YV_SMFV(9);
+        else YV_SMFV(16);
+#undef YV_SMFV
+        YV_LAUNCHED();
+    }
 #define YV_SMF(PL) YV_CUDA(yv_launch(softmax_fwd_kernel<PL>, grid, dim3(THREADS), 0, S(stream), s, ld_s, mask, rows, cols, \
                                      rows_per_pair, scale, pp, ld_p, plane_stride, drop_p, drop_site, rp))
     if (cols <= 96) YV_SMF(3);
@@ -1134,6 +1253,19 @@ extern "C" int yv_softmax_bwd(const float* p, const float* dpd, int64_t ld_s, in
     const dim3 grid((unsigned)((rows + WARPS - 1) / WARPS));
     auto* dp = reinterpret_cast<__nv_bfloat16*>(ds_planes);
     auto* rp = reinterpret_cast<const unsigned long long*>(rng);
+    const bool vec = g_softmax_vec && cols % 4 == 0 && ld_s % 4 == 0 && ld_p % 4 == 0 && plane_stride % 4 == 0 &&
+                     (((uintptr_t)p | (uintptr_t)dpd) & 15) == 0 && (((uintptr_t)ds_planes) & 7) == 0;
+    if (vec) {
+#define YV_SMBV(NV) YV_CUDA(yv_launch(softmax_bwd_vec_kernel<NV>, grid, dim3(THREADS), 0, S(stream), p, dpd, ld_s, rows, cols, \
+                                      scale, dp, ld_p, plane_stride, drop_p, drop_site, rp))
+        if (cols <= 128) YV_SMBV(1);
+        else if (cols <= 384) YV_SMBV(3);
+        else if (cols <= 640) YV_SMBV(5);
+        else if (cols <= 1152) YV_SMBV(9);
+        else YV_SMBV(16);
+#undef YV_SMBV
+        YV_LAUNCHED();
+    }
 #define YV_SMB(PL) YV_CUDA(yv_launch(softmax_bwd_kernel<PL>, grid, dim3(THREADS), 0, S(stream), p, dpd, ld_s, rows, cols, scale, \
                                      dp, ld_p, plane_stride, drop_p, drop_site, rp))
     if (cols <= 96) YV_SMB(3);
