@@ -73,3 +73,19 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert C.sizeof(m) == int(size), (name, C.sizeof(m), size)
         for f, off in zip(fields[name], offs):
             assert getattr(m, f).offset == int(off), (name, f, getattr(m, f).offset, off)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """The CUDA path has no fallback: without libyvb200.so, loading raises and names the build command."""
+    from yvb200 import lib, ops
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "libyvb200.so"))
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        lib.load()
+    # and the operator layer refuses host tensors instead of computing something else
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.rt("cpu")
+    import torch
+    from yvb200 import masking
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        masking.randomize_regions(torch.zeros(1, 2, 4), torch.zeros(1, 2, 3), torch.ones(1, 2, dtype=torch.long))
