@@ -160,6 +160,58 @@ int yv_softmax_bwd(const float* p, const float* dpd, int64_t ld_s, int64_t rows,
                    const uint64_t* rng, yv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * yv_attn_fwd / yv_attn_bwd: fused scaled-dot-product attention on tcgen05 (one launch each):
+ *   O = dropout(softmax(Q K^T * scale + mask[pair, key])) V
+ * replaces torch.matmul -> +mask -> nn.Softmax -> nn.Dropout -> torch.matmul of vilbert/vilbert.py:294-306
+ * (BertSelfAttention), :423-435 (BertImageSelfAttention) and :577-589 / :597-611 (the two directions of
+ * BertBiAttention) plus their autograd backward.  Scores and probabilities stay in TMEM / shared memory; the forward
+ * saves one log-sum-exp per query row and the backward recomputes the probabilities (same dropout mask: the counter
+ * RNG is keyed by (pair, head, query, key) exactly like yv_softmax_fwd).
+ * A YvHeadView is a [pairs, rows, heads*dh] view of a bf16 plane pair (e.g. the Q third of a fused Q|K|V projection
+ * output): element (pair, row, head, d) at ptr[pair*pair_stride + row*ld + head*dh + d], lo plane plane_stride later.
+ * dh must be 64 or 128 (yv_attn_supported); ptr 16-byte aligned; ld, pair_stride, plane_stride multiples of 8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* ptr;
+    int64_t ld, plane_stride, pair_stride;
+    int32_t rows, _pad;
+} YvHeadView;
+
+typedef struct {
+    int32_t pairs, heads, dh, passes;   /* passes: 1 (bf16) or 3 (bf16x3, also for P V) */
+    YvHeadView q, k, v;                 /* q.rows = Tq, k.rows = v.rows = Tk */
+    const float* mask;                  /* [pairs, Tk] additive (0 / -10000, vilbert/vilbert.py:1268-1287) or NULL */
+    float scale;                        /* 1 / sqrt(dh) */
+    float drop_p;
+    uint32_t drop_site, _pad;
+    const uint64_t* rng;
+    void* out_planes;                   /* context [pairs*Tq, heads*dh] as a plane pair (heads merged, :307-309) */
+    int64_t ld_out, out_plane_stride;
+    float* out32;                       /* optional fp32 copy of the context */
+    int64_t ld_out32;
+    float* lse;                         /* [pairs*heads*Tq] row log-sum-exp, input of yv_attn_bwd (may be NULL) */
+} YvAttnFwd;
+int yv_attn_supported(int32_t dh, int32_t passes);
+int yv_attn_fwd(const YvAttnFwd* a, yv_stream_t stream);
+
+typedef struct {
+    int32_t pairs, heads, dh, passes;
+    YvHeadView q, k, v;
+    YvHeadView dout, out;               /* gradient of the context and the forward's context, rows = Tq */
+    const float* mask;
+    float scale;
+    float drop_p;
+    uint32_t drop_site, _pad;
+    const uint64_t* rng;
+    const float* lse;
+    YvHeadView dq, dk, dv;              /* outputs (plane pairs); dq.rows = Tq, dk.rows = dv.rows = Tk */
+    void* workspace;                    /* ZERO-FILLED by the caller, yv_attn_bwd_workspace_bytes() bytes */
+    size_t workspace_bytes;
+} YvAttnBwd;
+size_t yv_attn_bwd_workspace_bytes(int32_t pairs, int32_t heads, int32_t dh, int32_t Tk);
+int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * embeddings
  *   text  (vilbert/vilbert.py:240-253): out[m] = word[tok[m]] + pos[m % T] + type[seg[m]]
  *   image (vilbert/vilbert.py:1361-1365): out[m] = W5.loc[0:5]+b5 + W4.loc[5:9]+b4 + W2.loc[9:11]+b2 + seq[loc[11]]

@@ -532,6 +532,21 @@ class BertEncoder(nn.Module):
 
     def forward(self, txt_embedding, image_embedding, txt_attention_mask, image_attention_mask,
                 co_attention_mask=None, output_all_encoded_layers=True, output_all_attention_masks=False):
+        if not txt_embedding.is_cuda:
+            return self._forward(txt_embedding, image_embedding, txt_attention_mask, image_attention_mask,
+                                 co_attention_mask, output_all_encoded_layers, output_all_attention_masks)
+        # the layers hand back attention probabilities only when the caller collects them: otherwise the fused
+        # attention kernels run and the probabilities never exist in memory
+        r = _cuda_ops(txt_embedding).rt(txt_embedding.device)
+        prev, r.want_probs = r.want_probs, bool(output_all_attention_masks)
+        try:
+            return self._forward(txt_embedding, image_embedding, txt_attention_mask, image_attention_mask,
+                                 co_attention_mask, output_all_encoded_layers, output_all_attention_masks)
+        finally:
+            r.want_probs = prev
+
+    def _forward(self, txt_embedding, image_embedding, txt_attention_mask, image_attention_mask,
+                 co_attention_mask=None, output_all_encoded_layers=True, output_all_attention_masks=False):
         v_start = t_start = 0
         all_t, all_v = [], []
         att_t, att_v, att_c = [], [], []

@@ -23,7 +23,7 @@ SYMBOLS = [
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
-    "yv_mask_tokens", "yv_mask_regions",
+    "yv_mask_tokens", "yv_mask_regions", "yv_attn_supported", "yv_attn_fwd", "yv_attn_bwd", "yv_attn_bwd_workspace_bytes",
 ]
 
 
@@ -44,6 +44,29 @@ class YvGemm(C.Structure):
                 ("ld_pl", C.c_int64), ("pl_sb0", C.c_int64), ("pl_sb1", C.c_int64), ("pl_plane_stride", C.c_int64),
                 ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("rng", C.c_void_p),
                 ("out32_zeroed", C.c_int32), ("_pad2", C.c_int32)]
+
+
+class YvHeadView(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("plane_stride", C.c_int64), ("pair_stride", C.c_int64),
+                ("rows", C.c_int32), ("_pad", C.c_int32)]
+
+
+class YvAttnFwd(C.Structure):
+    _fields_ = [("pairs", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32), ("passes", C.c_int32),
+                ("q", YvHeadView), ("k", YvHeadView), ("v", YvHeadView),
+                ("mask", C.c_void_p), ("scale", C.c_float), ("drop_p", C.c_float), ("drop_site", C.c_uint32),
+                ("_pad", C.c_uint32), ("rng", C.c_void_p),
+                ("out_planes", C.c_void_p), ("ld_out", C.c_int64), ("out_plane_stride", C.c_int64),
+                ("out32", C.c_void_p), ("ld_out32", C.c_int64), ("lse", C.c_void_p)]
+
+
+class YvAttnBwd(C.Structure):
+    _fields_ = [("pairs", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32), ("passes", C.c_int32),
+                ("q", YvHeadView), ("k", YvHeadView), ("v", YvHeadView), ("dout", YvHeadView), ("out", YvHeadView),
+                ("mask", C.c_void_p), ("scale", C.c_float), ("drop_p", C.c_float), ("drop_site", C.c_uint32),
+                ("_pad", C.c_uint32), ("rng", C.c_void_p), ("lse", C.c_void_p),
+                ("dq", YvHeadView), ("dk", YvHeadView), ("dv", YvHeadView),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class YvSplitSeg(C.Structure):
@@ -68,6 +91,8 @@ def load():
     lib.yv_last_error.restype = C.c_char_p
     lib.yv_version.restype = C.c_int
     lib.yv_launch_count.restype = C.c_uint64
+    if hasattr(lib, "yv_attn_bwd_workspace_bytes"):
+        lib.yv_attn_bwd_workspace_bytes.restype = C.c_size_t
     for name in SYMBOLS:
         if not hasattr(lib, name):
             raise RuntimeError(f"yvb200: {LIB_PATH} does not export {name}")
@@ -78,7 +103,8 @@ def load():
 #: bench.py's roofline leg: when True every entry point except yv_gemm returns without launching, so that a captured
 #: step contains the GEMM launches only (their operands are then uninitialised memory: timing only, never results)
 ONLY_GEMM = False
-_ALWAYS = {"yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_rng_advance"}
+_ALWAYS = {"yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_rng_advance",
+           "yv_attn_supported", "yv_attn_bwd_workspace_bytes"}
 
 
 class _LibProxy:
@@ -357,3 +383,44 @@ def mask_regions(features, probs, mask, p, targets, targets_mask, rows: int, F: 
                                   C.c_void_p(p.data_ptr()), C.c_void_p(targets.data_ptr()),
                                   C.c_void_p(targets_mask.data_ptr()), C.c_int64(rows), C.c_int32(F), C.c_int32(Cc),
                                   _stream()), "mask_regions")
+
+
+def head_view(p: Planes, col_off: int, rows_per_pair: int) -> YvHeadView:
+    """Columns [col_off, col_off + heads*dh) of a plane pair [pairs*rows_per_pair, ld] as [pairs, rows, heads*dh]."""
+    return YvHeadView(p.ptr(col_off), p.ld, p.plane_stride, rows_per_pair * p.ld, rows_per_pair, 0)
+
+
+def attn_supported(dh: int, passes: int) -> bool:
+    return bool(load().yv_attn_supported(C.c_int32(dh), C.c_int32(passes)))
+
+
+def attn_bwd_workspace_bytes(pairs: int, heads: int, dh: int, Tk: int) -> int:
+    return int(load().yv_attn_bwd_workspace_bytes(C.c_int32(pairs), C.c_int32(heads), C.c_int32(dh), C.c_int32(Tk)))
+
+
+def attn_fwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, mask, pairs: int, heads: int, dh: int, scale: float,
+             out: Planes, out32=None, lse=None, passes: int = 3, drop_p: float = 0.0, drop_site: int = 0, rng=None):
+    """Fused softmax(Q K^T * scale + mask) V (yv_attn_fwd); ``out`` receives the merged-head context as planes."""
+    a = YvAttnFwd()
+    a.pairs, a.heads, a.dh, a.passes = pairs, heads, dh, passes
+    a.q, a.k, a.v = q, k, v
+    a.mask, a.scale, a.drop_p, a.drop_site, a.rng = _p(mask), scale, drop_p, drop_site, _p(rng)
+    a.out_planes, a.ld_out, a.out_plane_stride = out.ptr(), out.ld, out.plane_stride
+    a.out32, a.ld_out32 = _p(out32), (out32.stride(0) if out32 is not None else 0)
+    a.lse = _p(lse)
+    _check(load().yv_attn_fwd(C.byref(a), _stream()), "attn_fwd")
+
+
+def attn_bwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, dout: YvHeadView, out: YvHeadView, mask, lse, pairs: int,
+             heads: int, dh: int, scale: float, dq: YvHeadView, dk: YvHeadView, dv: YvHeadView, workspace: torch.Tensor,
+             passes: int = 3, drop_p: float = 0.0, drop_site: int = 0, rng=None):
+    """Fused attention backward (yv_attn_bwd); ``workspace`` is a zero-filled byte tensor of
+    ``attn_bwd_workspace_bytes`` bytes."""
+    a = YvAttnBwd()
+    a.pairs, a.heads, a.dh, a.passes = pairs, heads, dh, passes
+    a.q, a.k, a.v, a.dout, a.out = q, k, v, dout, out
+    a.mask, a.scale, a.drop_p, a.drop_site, a.rng = _p(mask), scale, drop_p, drop_site, _p(rng)
+    a.lse = _p(lse)
+    a.dq, a.dk, a.dv = dq, dk, dv
+    a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    _check(load().yv_attn_bwd(C.byref(a), _stream()), "attn_bwd")

@@ -75,6 +75,12 @@ class Runtime:
         self.defer_wgrad_allowed = os.environ.get("YVB200_DEFER_WGRAD", "1") != "0"
         self.early_zero = os.environ.get("YVB200_EARLY_ZERO", "1") != "0"
         self._join_queued = False
+        # fused attention kernels (yv_attn_fwd / yv_attn_bwd): used when the caller does not need the attention
+        # probabilities.  ``want_probs`` is set by BertEncoder.forward for the duration of a call (True when
+        # output_all_attention_masks); None = a sub-module called on its own, which returns probabilities like the
+        # reference and therefore takes the un-fused chain.  YVB200_FUSED_ATTN=0 forces the un-fused chain everywhere.
+        self.fused_attention = os.environ.get("YVB200_FUSED_ATTN", "1") != "0"
+        self.want_probs: Optional[bool] = None
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
         self.main_priority = -1 if prio else 0
         self.helper_priority = 0
@@ -387,6 +393,34 @@ class _EarlyOut:
         return self.zeroed
 
 
+class _ZeroedBytes:
+    """Zero-filled byte scratch; like ``_EarlyOut`` the fill runs on a forked stream as soon as the object is created and
+    ``ready()`` orders the issuing stream after it right before the consumer is launched."""
+    __slots__ = ("t", "_z", "_dev")
+
+    def __init__(self, r: "Runtime", nbytes: int, device):
+        self.t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self._dev = device
+        self._z = None
+        if r.concurrent and r.early_zero:
+            cur = torch.cuda.current_stream(device)
+            self._z = r.fork(2)
+            self._z.wait_stream(cur)
+            with torch.cuda.stream(self._z):
+                self.t.zero_()
+            self.t.record_stream(self._z)
+        else:
+            self.t.zero_()
+
+    def ready(self) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self._dev)
+        if self._z is not None:
+            cur.wait_stream(self._z)
+            self._z = None
+        self.t.record_stream(cur)
+        return self.t
+
+
 def _keep_for(side: torch.cuda.Stream, *objs):
     """Tensors consumed (or produced) by work left running on ``side``: the caching allocator must not hand their
     memory to a later allocation of the issuing stream before that work has run."""
@@ -610,13 +644,65 @@ class HeadView:
         return L.operand(self.p.ptr(self.off), dh, self.S, self.p.ld, self.p.plane_stride, mn_major, heads, dh, pairs,
                          self.S * self.p.ld)
 
+    def view(self):
+        return L.head_view(self.p, self.off, self.S)
+
 
 def _score_operand(p: Planes, Tq: int, Tk: int, ldS: int, pairs: int, heads: int, mn_major: bool):
     return L.operand(p.ptr(), Tk, Tq, ldS, p.plane_stride, mn_major, heads, Tq * ldS, pairs, heads * Tq * ldS)
 
 
+class _AttnSaved:
+    """What an attention forward leaves for its backward: the row log-sum-exp (fused kernels, probabilities are
+    recomputed) or the probabilities and their dropped bf16 planes (un-fused chain)."""
+    __slots__ = ("fused", "lse", "mask", "ctxp", "P", "Pp")
+
+    def __init__(self, fused, lse=None, mask=None, ctxp=None, P=None, Pp=None):
+        self.fused, self.lse, self.mask, self.ctxp, self.P, self.Pp = fused, lse, mask, ctxp, P, Pp
+
+    def keep_for(self, side):
+        _keep_for(side, self.lse, self.P, self.Pp)
+
+
+def _use_fused_attention(r: Runtime, dh: int) -> bool:
+    return r.fused_attention and r.want_probs is False and L.attn_supported(dh, r.attn_passes)
+
+
 def _attn_fwd(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Tensor, pairs: int, heads: int, dh: int,
-              drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]):
+              drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]) -> _AttnSaved:
+    """softmax(q k^T / sqrt(dh) + mask) v -> ``ctxp`` (merged heads): one fused launch, or GEMM -> softmax -> GEMM when
+    the probabilities themselves are wanted (or the head size has no fused kernel)."""
+    if _use_fused_attention(r, dh):
+        lse = _f32(pairs * heads * q.S, device=mask.device)
+        L.attn_fwd(q.view(), k.view(), v.view(), mask, pairs, heads, dh, 1.0 / math.sqrt(dh), ctxp, ctx32, lse,
+                   passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=r.rng)
+        return _AttnSaved(True, lse=lse, mask=mask, ctxp=ctxp)
+    P, Pp = _attn_fwd_unfused(r, q, k, v, mask, pairs, heads, dh, drop_p, site, ctxp, ctx32)
+    return _AttnSaved(False, P=P, Pp=Pp)
+
+
+def _attn_bwd(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, saved: _AttnSaved, pairs: int, heads: int,
+              dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView, fork_ok: bool = True,
+              workspace: Optional["_ZeroedBytes"] = None):
+    if saved.fused:
+        ws = workspace if workspace is not None else _ZeroedBytes(r, L.attn_bwd_workspace_bytes(pairs, heads, dh, k.S),
+                                                                  dOp.keep.device)
+        L.attn_bwd(q.view(), k.view(), v.view(), L.head_view(dOp, 0, q.S), L.head_view(saved.ctxp, 0, q.S), saved.mask,
+                   saved.lse, pairs, heads, dh, 1.0 / math.sqrt(dh), dq.view(), dk.view(), dv.view(), ws.ready(),
+                   passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=r.rng)
+        return
+    _attn_bwd_unfused(r, dOp, q, k, v, saved.P, saved.Pp, pairs, heads, dh, drop_p, site, dq, dk, dv, fork_ok)
+
+
+def _attn_workspace(r: Runtime, saved: _AttnSaved, pairs: int, heads: int, dh: int, Tk: int, device):
+    """Zero-filled scratch of the fused attention backward, filled early (off the dependency chain)."""
+    if not saved.fused:
+        return None
+    return _ZeroedBytes(r, L.attn_bwd_workspace_bytes(pairs, heads, dh, Tk), device)
+
+
+def _attn_fwd_unfused(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Tensor, pairs: int, heads: int, dh: int,
+                      drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]):
     Tq, Tk = q.S, k.S
     ldS = (Tk + 7) // 8 * 8
     dev = mask.device
@@ -633,9 +719,9 @@ def _attn_fwd(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Ten
     return S, Pp
 
 
-def _attn_bwd(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, P: torch.Tensor, Pp: Planes, pairs: int,
-              heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView,
-              fork_ok: bool = True):
+def _attn_bwd_unfused(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, P: torch.Tensor, Pp: Planes,
+                      pairs: int, heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView,
+                      fork_ok: bool = True):
     """dP -> softmax' -> dQ on the issuing stream; dV (needs only P and dO) and dK (needs dS) on a forked stream when
     ``fork_ok`` (callers that already run this function on a forked stream pass False)."""
     Tq, Tk = q.S, k.S
@@ -708,27 +794,26 @@ class SelfAttentionFn(Function):
         c32 = _f32(M, H, device=x.device)
         cp = Planes.empty(M, H, x.device)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        P, Pp = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, c32)
-        ctx.r, ctx.xp, ctx.wp, ctx.qkv, ctx.Pp, ctx.spec = r, xp, wp, qkv, Pp, spec
+        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, c32)
+        ctx.r, ctx.xp, ctx.wp, ctx.qkv, ctx.att, ctx.spec = r, xp, wp, qkv, att, spec
         ctx.dims = (pairs, S, K, H, heads, dh)
-        ctx.save_for_backward(P)
         spec.out_planes = cp
-        spec.probs = P
+        spec.probs = att.P
         return c32.view(pairs, S, H)
 
     @staticmethod
     def backward(ctx, dc):
         r, spec = ctx.r, ctx.spec
         pairs, S, K, H, heads, dh = ctx.dims
-        (P,) = ctx.saved_tensors
         M = pairs * S
         dev = dc.device
+        ws = _attn_workspace(r, ctx.att, pairs, heads, dh, S, dev)
         dOp = L.split_planes(_c2d(dc))
         dqkv = Planes.empty(M, 3 * H, dev)
         qkv = ctx.qkv
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        _attn_bwd(r, dOp, q, k, v, P, ctx.Pp, pairs, heads, dh, spec.drop_p, spec.site,
-                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
+        _attn_bwd(r, dOp, q, k, v, ctx.att, pairs, heads, dh, spec.drop_p, spec.site,
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), workspace=ws)
         dx, dW, db = _linear_bwd(r, dqkv, ctx.xp, ctx.wp, M, 3 * H, K, dev, ctx.needs_input_grad[0], True, defer=True)
         return ((dx.view(pairs, S, K) if dx is not None else None), None,
                 dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:], None)
@@ -770,7 +855,7 @@ class AttnBlockFn(Function):
                out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
         cp = Planes.empty(M, H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        P, Pp = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None)
+        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None)
         s = s_out.t
         L.gemm(M, H, H, L.op_of(cp), L.op_of(wo), passes=r.passes, bias=bo, residual=x2, out32=s, ld_out=H,
                drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=r.rng, out32_zeroed=s_out.ready())
@@ -779,22 +864,23 @@ class AttnBlockFn(Function):
         stats = _f32(M, 2, device=dev)
         L.layernorm_fwd(s, gamma, beta, LN_EPS, z, zp, stats, M, H)
         ctx.r, ctx.spec = r, spec
-        ctx.keep = (xp, wqkv, wo, qkv, Pp, cp)
+        ctx.keep = (xp, wqkv, wo, qkv, att, cp)
         ctx.dims = (pairs, S, K, H, heads, dh)
-        ctx.save_for_backward(P, s, stats, gamma)
+        ctx.save_for_backward(s, stats, gamma)
         spec.out_planes = zp
-        spec.probs = P
+        spec.probs = att.P
         return z.view(pairs, S, H)
 
     @staticmethod
     def backward(ctx, dz):
         r, spec = ctx.r, ctx.spec
         pairs, S, K, H, heads, dh = ctx.dims
-        xp, wqkv, wo, qkv, Pp, cp = ctx.keep
-        P, s, stats, gamma = ctx.saved_tensors
+        xp, wqkv, wo, qkv, att, cp = ctx.keep
+        s, stats, gamma = ctx.saved_tensors
         M = pairs * S
         dev = dz.device
         dx_out = _EarlyOut(r, M, K, 3 * H, dev) if ctx.needs_input_grad[0] else None
+        ws = _attn_workspace(r, att, pairs, heads, dh, S, dev)
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, d(out bias)
@@ -812,8 +898,8 @@ class AttnBlockFn(Function):
                pl_plane_stride=dOp.plane_stride)
         dqkv = Planes.empty(M, 3 * H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        _attn_bwd(r, dOp, q, k, v, P, Pp, pairs, heads, dh, spec.drop_p, spec.site,
-                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S))
+        _attn_bwd(r, dOp, q, k, v, att, pairs, heads, dh, spec.drop_p, spec.site,
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), workspace=ws)
         if side is not cur and r.defer_wgrad:
             _keep_for(side, dsp, cp, dWo)
             r.defer_join()
@@ -965,27 +1051,26 @@ class BiAttentionFn(Function):
         cur.wait_stream(side)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            P1, P1p = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
-        P2, P2p = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2)
+            att1 = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
+        att2 = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2)
         cur.wait_stream(side)
-        for t_ in (P1, P1p.keep):
-            t_.record_stream(cur)
+        att1.keep_for(cur)
         ctx.r, ctx.spec = r, spec
-        ctx.keep = (xvp, xtp, w1, w2, qkv1, qkv2, P1p, P2p)
+        ctx.keep = (xvp, xtp, w1, w2, qkv1, qkv2, att1, att2)
         ctx.dims = (pairs, V, T, Kv, Kt, H, heads, dh)
-        ctx.save_for_backward(P1, P2)
         spec.out_planes = (c1p, c2p)
-        spec.probs = (P1, P2)
+        spec.probs = (att1.P, att2.P)
         return c1.view(pairs, T, H), c2.view(pairs, V, H)
 
     @staticmethod
     def backward(ctx, dc1, dc2):
         r, spec = ctx.r, ctx.spec
         pairs, V, T, Kv, Kt, H, heads, dh = ctx.dims
-        xvp, xtp, w1, w2, qkv1, qkv2, P1p, P2p = ctx.keep
-        P1, P2 = ctx.saved_tensors
+        xvp, xtp, w1, w2, qkv1, qkv2, att1, att2 = ctx.keep
         dev = dc1.device
         Mv, Mt = pairs * V, pairs * T
+        ws1 = _attn_workspace(r, att1, pairs, heads, dh, V, dev)
+        ws2 = _attn_workspace(r, att2, pairs, heads, dh, T, dev)
         dxv_out = _EarlyOut(r, Mv, Kv, 3 * H, dev) if ctx.needs_input_grad[0] else None
         dxt_out = _EarlyOut(r, Mt, Kt, 3 * H, dev) if ctx.needs_input_grad[2] else None
         dO1 = L.split_planes(_c2d(dc1))
@@ -1000,8 +1085,8 @@ class BiAttentionFn(Function):
         side = r.fork() if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            _attn_bwd(r, dO1, q2, k1, v1, P1, P1p, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1)
-        _attn_bwd(r, dO2, q1, k2, v2, P2, P2p, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2)
+            _attn_bwd(r, dO1, q2, k1, v1, att1, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1, workspace=ws1)
+        _attn_bwd(r, dO2, q1, k2, v2, att2, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2, workspace=ws2)
         cur.wait_stream(side)
         dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True, defer=True,
                                      dx_out=dxv_out)
