@@ -205,10 +205,12 @@ typedef struct {
     const uint64_t* rng;
     const float* lse;
     YvHeadView dq, dk, dv;              /* outputs (plane pairs); dq.rows = Tq, dk.rows = dv.rows = Tk */
-    void* workspace;                    /* ZERO-FILLED by the caller, yv_attn_bwd_workspace_bytes() bytes */
+    void* workspace;                    /* scratch (contents irrelevant), yv_attn_bwd_workspace_bytes() bytes: per-query-
+                                           tile partial dK / dV, added up by the last CTA of each (pair, head) */
     size_t workspace_bytes;
+    uint32_t* tickets;                  /* [pairs*heads], zero before the first launch; every launch leaves it zero */
 } YvAttnBwd;
-size_t yv_attn_bwd_workspace_bytes(int32_t pairs, int32_t heads, int32_t dh, int32_t Tk);
+size_t yv_attn_bwd_workspace_bytes(int32_t pairs, int32_t heads, int32_t dh, int32_t Tq, int32_t Tk);
 int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

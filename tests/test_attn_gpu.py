@@ -102,10 +102,11 @@ def test_fused_attention_forward_backward_match_fp64(pairs, heads, dh, Tq, Tk):
     assert _rel(lse.view(pairs, heads, Tq), lse_ref) < 1e-5
     dq = L.Planes.empty(pairs * Tq, H, "cuda")
     dkv = L.Planes.empty(pairs * Tk, 2 * H, "cuda")
-    ws = torch.zeros(L.attn_bwd_workspace_bytes(pairs, heads, dh, Tk), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(L.attn_bwd_workspace_bytes(pairs, heads, dh, Tq, Tk), dtype=torch.uint8, device="cuda")
+    tk = torch.zeros(pairs * heads, dtype=torch.int32, device="cuda")
     L.attn_bwd(L.head_view(qp, 0, Tq), L.head_view(kp, H, Tk), L.head_view(kp, 2 * H, Tk), L.head_view(dOp, 0, Tq),
                L.head_view(out, 0, Tq), mask, lse, pairs, heads, dh, scale, L.head_view(dq, 0, Tq),
-               L.head_view(dkv, 0, Tk), L.head_view(dkv, H, Tk), ws)
+               L.head_view(dkv, 0, Tk), L.head_view(dkv, H, Tk), ws, tk)
     torch.cuda.synchronize()
     assert _rel(dq.float(), dq_ref) < 5e-5
     assert _rel(dkv.float()[:, :H], dk_ref) < 5e-5
@@ -144,11 +145,11 @@ def test_fused_attention_with_dropout_matches_unfused_kernels(pairs, heads, dh, 
     dOp = _planes(dO)
     # un-fused chain
     c_un = L.Planes.empty(pairs * Tq, H, "cuda")
-    P, Pp = ops._attn_fwd_unfused(r, q, k, v, mask, pairs, heads, dh, p_drop, site, c_un, None)
+    P, Pp = ops._attn_fwd_unfused(r, q, k, v, mask, pairs, heads, dh, p_drop, site, c_un, None, r.rng)
     d_un = L.Planes.empty(pairs * Tq, H, "cuda")
     dkv_un = L.Planes.empty(pairs * Tk, 2 * H, "cuda")
     ops._attn_bwd_unfused(r, dOp, q, k, v, P, Pp, pairs, heads, dh, p_drop, site, ops.HeadView(d_un, 0, Tq),
-                          ops.HeadView(dkv_un, 0, Tk), ops.HeadView(dkv_un, H, Tk))
+                          ops.HeadView(dkv_un, 0, Tk), ops.HeadView(dkv_un, H, Tk), rng=r.rng)
     # fused
     c_f = L.Planes.empty(pairs * Tq, H, "cuda")
     lse = torch.empty(pairs * heads * Tq, device="cuda")
@@ -157,10 +158,11 @@ def test_fused_attention_with_dropout_matches_unfused_kernels(pairs, heads, dh, 
                c_f, None, lse, drop_p=p_drop, drop_site=site, rng=r.rng)
     d_f = L.Planes.empty(pairs * Tq, H, "cuda")
     dkv_f = L.Planes.empty(pairs * Tk, 2 * H, "cuda")
-    ws = torch.zeros(L.attn_bwd_workspace_bytes(pairs, heads, dh, Tk), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(L.attn_bwd_workspace_bytes(pairs, heads, dh, Tq, Tk), dtype=torch.uint8, device="cuda")
+    tk = torch.zeros(pairs * heads, dtype=torch.int32, device="cuda")
     L.attn_bwd(L.head_view(qp, 0, Tq), L.head_view(kp, H, Tk), L.head_view(kp, 2 * H, Tk), L.head_view(dOp, 0, Tq),
                L.head_view(c_f, 0, Tq), mask, lse, pairs, heads, dh, scale, L.head_view(d_f, 0, Tq),
-               L.head_view(dkv_f, 0, Tk), L.head_view(dkv_f, H, Tk), ws, drop_p=p_drop, drop_site=site, rng=r.rng)
+               L.head_view(dkv_f, 0, Tk), L.head_view(dkv_f, H, Tk), ws, tk, drop_p=p_drop, drop_site=site, rng=r.rng)
     torch.cuda.synchronize()
     assert _rel(c_f.float(), c_un.float()) < 1e-4
     assert _rel(d_f.float(), d_un.float()) < 1e-4

@@ -118,12 +118,13 @@ def test_train_mode_dropout_statistics():
     model = build_lily(cfg, args, device="cuda").train()
     batch = _to_dev(synth.make_batch("micro", seed=1), "cuda")
     inp = synth.model_inputs(batch)
-    state = r.rng.clone()
+    state = r.rng_state()
     o1 = model(*inp)["vision"].detach().clone()
-    r.rng.copy_(state)
+    r.set_rng_state(state)
     o2 = model(*inp)["vision"].detach().clone()
     assert torch.equal(o1, o2)
-    r.advance_rng()
+    # every training forward advances the step counter by itself (the unmodified reference loop never touches the RNG):
+    # two consecutive forwards draw different masks
     o3 = model(*inp)["vision"].detach().clone()
     assert not torch.equal(o1, o3)
     model.eval()
@@ -131,14 +132,66 @@ def test_train_mode_dropout_statistics():
     assert float((o1 - oe).norm() / oe.norm()) > 1e-3          # dropout really perturbs the output
     # backward runs in train mode and regenerates the same masks
     model.train()
-    r.rng.copy_(state)
+    r.set_rng_state(state)
     torch.manual_seed(3)            # the [N,1024] pooled dropout of the task wrapper stays on torch's generator
     out = model(*inp)
     losses.total_loss(losses.step_losses(batch, out, args, True), args).backward()
     g1 = model.bert.encoder.layer[0].attention.self.query.weight.grad.clone()
     model.zero_grad()
-    r.rng.copy_(state)
+    r.set_rng_state(state)
     torch.manual_seed(3)
     out = model(*inp)
     losses.total_loss(losses.step_losses(batch, out, args, True), args).backward()
     assert torch.allclose(g1, model.bert.encoder.layer[0].attention.self.query.weight.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_backward_regenerates_the_masks_of_its_own_forward():
+    """Two training forwards before the first backward (e.g. two micro-batches summed into one loss): each backward must
+    regenerate the dropout masks of ITS forward, not those of whichever forward ran last."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from yvb200 import ops
+    r = ops.rt("cuda")
+    cfg = synth.CONFIGS["micro"]
+    args = synth.workload_args("micro")
+    model = build_lily(cfg, args, device="cuda").train()
+    batch = _to_dev(synth.make_batch("micro", seed=1), "cuda")
+    inp = synth.model_inputs(batch)
+    w = model.bert.encoder.layer[0].attention.self.query.weight
+    state = r.rng_state()
+    torch.manual_seed(3)
+    out = model(*inp)
+    losses.total_loss(losses.step_losses(batch, out, args, True), args).backward()
+    want = w.grad.clone()
+    model.zero_grad()
+    r.set_rng_state(state)
+    torch.manual_seed(3)
+    out = model(*inp)
+    loss = losses.total_loss(losses.step_losses(batch, out, args, True), args)
+    with torch.no_grad():
+        model(*inp)                      # an unrelated training-mode forward in between advances the counter
+    loss.backward()
+    assert torch.allclose(want, w.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_weight_planes_follow_in_place_data_updates():
+    """The reference's AdamW updates ``p.data`` in place (vilbert/optimization.py:176-187), which does not bump the
+    tensor version: the start-of-forward refresh must re-split the weights anyway."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = synth.CONFIGS["micro"]
+    args = synth.workload_args("micro")
+    model = build_lily(cfg, args, device="cuda").eval()
+    batch = _to_dev(synth.make_batch("micro", seed=1), "cuda")
+    inp = synth.model_inputs(batch)
+    o1 = model(*inp)["ranking"].detach().clone()
+    w = model.bert.encoder.layer[0].attention.self.query.weight
+    v0 = w._version
+    w.data.mul_(1.5)                     # what an optimizer step through .data looks like
+    assert w._version == v0
+    o2 = model(*inp)["ranking"].detach().clone()          # autograd is on: every weight is re-split
+    ref = build_lily(cfg, args, device="cuda").eval()
+    ref.load_state_dict(model.state_dict())
+    o3 = ref(*inp)["ranking"].detach()
+    assert not torch.equal(o1, o2)
+    assert torch.allclose(o2, o3, rtol=1e-5, atol=1e-6)

@@ -8,9 +8,11 @@
 // GEMM -> fp32 scores in HBM -> softmax kernel -> bf16 planes in HBM -> GEMM (3 launches forward, 6 backward).
 //
 // Work decomposition: one CTA per (128-query tile, head, pair); keys are streamed in chunks of 64.
-//   warp 8 (one lane): TMA producer and tcgen05.mma issuer.  Q (and dO) tiles stay resident in shared memory, K / V
-//                      chunks stream through single buffers (the next K chunk is loaded as soon as S = Q K^T of the
-//                      current one has retired, the next V chunk as soon as P V has).
+//   warps 8, 9 (one lane each): TMA producers and tcgen05.mma issuers.  Issuing a 128x64x16 MMA costs one thread about
+//                      60 cycles (descriptor moves to uniform registers), twice its tensor-pipe time, so the products
+//                      of a chunk are split over two issuing threads: forward S = Q K^T (warp 8, K double-buffered)
+//                      and O += P V (warp 9); backward S, dV^T (warp 8) and dPd, dK^T, dQ (warp 9).  Q (and dO) tiles
+//                      stay resident in shared memory, K / V chunks stream.
 //   warps 0-7        : softmax.  Warp w owns TMEM lanes 32*(w&3).. (query rows) and key columns 32*(w>>2).. of the
 //                      chunk: S comes out of TMEM with one tcgen05.ld.32x32b.x32, exp / dropout / hi-lo split run in
 //                      registers, P goes back to shared memory in the 128B-swizzled K-major operand layout and is the
@@ -20,8 +22,9 @@
 // hi*hi only (PASSES = 1).  A [rows x 64] 128B-swizzled tile is addressed as a K-major operand (contraction along the
 // 64-element direction) or as an MN-major operand (contraction along rows) just by the descriptor, so the backward
 // needs no transposed copies: dV^T = dO^T Pd, dK^T = Q^T dS and dQ = dS K all read the tiles the forward products use.
-// dK / dV of one (pair, head) receive contributions from every query tile: they are reduced in an fp32 scratch with
-// red.global.add and converted to planes by the last CTA of that (pair, head) (atomic ticket).
+// dK / dV of one (pair, head) receive contributions from every query tile: each tile stores its partial sums to its own
+// fp32 slab of the workspace (plain coalesced stores; global reductions run at ~1 lane per clock and SM) and the last CTA
+// of that (pair, head) -- atomic ticket -- adds the slabs and writes the planes.
 // Dropout masks use the same counter-based hash and element index (row * Tk + key) as yv_softmax_fwd / _bwd.
 #include "yv_gemm_common.cuh"
 
@@ -29,11 +32,19 @@ namespace {
 
 constexpr int QT = 128;            // query rows per CTA (UMMA M)
 constexpr int KC = 64;             // keys per chunk (UMMA N of the score product, one 128-byte swizzled row)
-constexpr int ATT_THREADS = 288;   // 8 softmax warps + 1 control warp
+constexpr int ATT_THREADS = 320;   // 8 softmax warps + 2 issuer warps (TMA + tcgen05.mma, one lane each)
 constexpr int SM_THREADS = 256;
 constexpr uint32_t Q_BLK = QT * 128;    // bytes of a [128 rows x 64 bf16] block
 constexpr uint32_t KV_BLK = KC * 128;   // bytes of a [64 rows x 64 bf16] block
 constexpr float RESCALE_THRESHOLD = 8.f;
+
+// developer timing (tools/attn_timing.cu): clock64 stamps of CTA (0, 0, 0)
+#ifdef YV_ATTN_TIMING
+__device__ long long yv_adbg[128];
+#define YV_AT(i) do { if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (i) < 128) yv_adbg[i] = clock64(); } while (0)
+#else
+#define YV_AT(i)
+#endif
 
 struct PlaneView {
     __nv_bfloat16* ptr;            // hi plane, element (row 0, head 0, d 0)
@@ -127,13 +138,7 @@ YV_DEVINL void store_tile_row(uint32_t tile, int row, int half, const float* x) 
     for (int g = 0; g < 4; ++g) {
         uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            yv_split(x[8 * g + 2 * e], h0, l0);
-            yv_split(x[8 * g + 2 * e + 1], h1, l1);
-            hi[e] = pack_bf16(h0, h1);
-            lo[e] = pack_bf16(l0, l1);
-        }
+        for (int e = 0; e < 4; ++e) yv_split2(x[8 * g + 2 * e], x[8 * g + 2 * e + 1], hi[e], lo[e]);
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((4 * half + g) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
                      "r"(hi[3])
@@ -145,29 +150,60 @@ YV_DEVINL void store_tile_row(uint32_t tile, int row, int half, const float* x) 
     }
 }
 
-// 32 consecutive fp32 values -> hi / lo planes at `dst` (16-byte aligned), optional fp32 copy
-template <int PASSES>
-YV_DEVINL void store_row32(__nv_bfloat16* dst, long long plane_stride, float* dst32, const float* x) {
+// Output tiles ([128 rows x DH], thread = row in registers) leave through a swizzled shared-memory staging area so that
+// the global stores are whole rows: 16-byte chunk c of row r of plane pl sits at pl * 128 * DH * 2 + r * DH * 2 +
+// ((c ^ (r & 7)) << 4).  stage_row32 writes 32 consecutive columns of one row, copy_out_rows writes the tile.
+template <int DH>
+YV_DEVINL void stage_row32(uint32_t stage, int row, int col0, const float* x) {
+    constexpr uint32_t ROW_B = DH * 2, PLANE_B = QT * ROW_B;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        uint4 hv, lv;
-        uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
-        uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            yv_split(x[8 * g + 2 * e], h0, l0);
-            yv_split(x[8 * g + 2 * e + 1], h1, l1);
-            hp[e] = pack_bf16(h0, h1);
-            lp[e] = pack_bf16(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(dst + 8 * g) = hv;
-        *reinterpret_cast<uint4*>(dst + plane_stride + 8 * g) = lv;   // the lo plane is kept current in both modes
+        for (int e = 0; e < 4; ++e) yv_split2(x[8 * g + 2 * e], x[8 * g + 2 * e + 1], hi[e], lo[e]);
+        const uint32_t off = (uint32_t)row * ROW_B + (uint32_t)((((col0 >> 3) + g) ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                     "r"(hi[3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + PLANE_B + off), "r"(lo[0]), "r"(lo[1]),
+                     "r"(lo[2]), "r"(lo[3])
+                     : "memory");
     }
-    if (dst32) {
+}
+template <int DH>
+YV_DEVINL void copy_out_rows(uint32_t stage, const PlaneView& out, long long grow0, int rows_valid, int head, int warp,
+                             int lane) {
+    constexpr uint32_t ROW_B = DH * 2, PLANE_B = QT * ROW_B;
+    constexpr int CPR = DH / 8;                 // 16-byte chunks per row
+    constexpr int RPI = 32 / CPR;               // rows per warp instruction
+    const int c = lane % CPR, rsub = lane / CPR;
+#pragma unroll 2
+    for (int r = warp * RPI + rsub; r < rows_valid; r += 8 * RPI) {
+        const uint32_t off = (uint32_t)r * ROW_B + (uint32_t)((c ^ (r & 7)) << 4);
+        __nv_bfloat16* dst = out.ptr + (grow0 + r) * out.ld + head * DH + c * 8;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(dst32 + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+        for (int pl = 0; pl < 2; ++pl) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(stage + pl * PLANE_B + off));
+            *reinterpret_cast<uint4*>(dst + pl * out.plane_stride) = v;
+        }
+    }
+}
+
+// additive mask values of 32 consecutive keys, -inf past Tk (branch-free: clamped address, predicated select), issued
+// before the thread waits for the scores so that their latency is hidden behind the MMA
+YV_DEVINL void load_mask32(const float* mrow, int key0, int Tk, float* mk) {
+    if (mrow) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int key = key0 + i;
+            const float v = __ldg(mrow + min(key, Tk - 1));
+            mk[i] = key < Tk ? v : -INFINITY;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mk[i] = (key0 + i) < Tk ? 0.f : -INFINITY;
     }
 }
 
@@ -177,13 +213,15 @@ struct FwdCfg {
     static constexpr int DB = DH / 64;
     static constexpr uint32_t HEADER = 4096;                       // barriers, TMEM slot, row-statistic exchange
     static constexpr uint32_t SQ = 0;
-    static constexpr uint32_t SK = SQ + PL * DB * Q_BLK;
-    static constexpr uint32_t SV = SK + PL * DB * KV_BLK;
+    static constexpr uint32_t K_BUF = PL * DB * KV_BLK;             // one K chunk (all planes / head-dimension blocks)
+    static constexpr uint32_t SK = SQ + PL * DB * Q_BLK;            // two K buffers
+    static constexpr uint32_t SV = SK + 2 * K_BUF;
     static constexpr uint32_t SP = SV + PL * DB * KV_BLK;
     static constexpr uint32_t TILES = SP + PL * Q_BLK;
     static constexpr uint32_t SMEM = HEADER + 1024 + TILES;
     static constexpr int TMEM_COLS = 256;                           // S0 [0,64) S1 [64,128) O [128, 128 + DH)
     static_assert(SMEM <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+    static_assert(TILES >= 2u * QT * DH * 2, "the operand tiles double as the output staging area");
 };
 
 // ------------------------------------------------------------------------------------------- forward
@@ -194,14 +232,17 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     using C = FwdCfg<DH, PASSES>;
     constexpr int PL = C::PL, DB = C::DB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);         // 0 Q, 1 K, 2 V, 3-4 S[2], 5 P, 6 O
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 64);
+    // barriers: 0 Q landed, 1-2 K[2] landed, 3 V landed, 4-5 S[2] retired, 6-7 S[2] read by the softmax warps,
+    //           8 P written (+ O rescaled), 9 P V retired
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 96);
     float* xm = reinterpret_cast<float*>(smem_raw + 128);           // [2 (chunk parity)][2 (column half)][128 rows]
     float* xl = xm + 2 * 2 * QT;                                    // [2][128]
     const uint32_t tiles = (smem_u32(smem_raw) + C::HEADER + 1023u) & ~1023u;
     const uint32_t sQ = tiles + C::SQ, sK = tiles + C::SK, sV = tiles + C::SV, sP = tiles + C::SP;
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * i; };
+    constexpr int B_Q = 0, B_K = 1, B_V = 3, B_S = 4, B_SFREE = 6, B_P = 8, B_O = 9;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x, head = blockIdx.y, pair = blockIdx.z;
@@ -210,13 +251,16 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     yv_pdl_trigger();
 
     if (threadIdx.x == 0) {
-        mbar_init(bar(0), 1);
-        mbar_init(bar(1), 1);
-        mbar_init(bar(2), 1);
-        mbar_init(bar(3), 1);
-        mbar_init(bar(4), 1);
-        mbar_init(bar(5), 8);
-        mbar_init(bar(6), 1);
+        mbar_init(bar(B_Q), 1);
+        mbar_init(bar(B_K), 1);
+        mbar_init(bar(B_K + 1), 1);
+        mbar_init(bar(B_V), 1);
+        mbar_init(bar(B_S), 1);
+        mbar_init(bar(B_S + 1), 1);
+        mbar_init(bar(B_SFREE), 8);
+        mbar_init(bar(B_SFREE + 1), 8);
+        mbar_init(bar(B_P), 8);
+        mbar_init(bar(B_O), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_k) : "memory");
@@ -235,42 +279,56 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t tmem_o = tmem + 128;
     yv_pdl_wait();
 
+    auto load_kv = [&](const CUtensorMap* map, uint32_t dst, uint32_t b, int chunk) {
+        mbar_expect_tx(b, PL * DB * KV_BLK);
+#pragma unroll
+        for (int pl = 0; pl < PL; ++pl)
+#pragma unroll
+            for (int d = 0; d < DB; ++d)
+                tma_load_5d(dst + (pl * DB + d) * KV_BLK, map, b, d * 64, chunk * KC, head, pair, pl);
+    };
+
     if (warp == 8) {
         if (lane == 0) {
-            // ===================================== TMA + MMA issue =====================================
-            auto load_kv = [&](const CUtensorMap* map, uint32_t dst, uint32_t b, int chunk) {
-                mbar_expect_tx(b, PL * DB * KV_BLK);
-#pragma unroll
-                for (int pl = 0; pl < PL; ++pl)
-#pragma unroll
-                    for (int d = 0; d < DB; ++d)
-                        tma_load_5d(dst + (pl * DB + d) * KV_BLK, map, b, d * 64, chunk * KC, head, pair, pl);
-            };
-            mbar_expect_tx(bar(0), PL * DB * Q_BLK);
+            // ============================ Q / K loads, S = Q K^T (runs up to two chunks ahead) ============================
+            mbar_expect_tx(bar(B_Q), PL * DB * Q_BLK);
 #pragma unroll
             for (int pl = 0; pl < PL; ++pl)
 #pragma unroll
                 for (int d = 0; d < DB; ++d)
-                    tma_load_5d(sQ + (pl * DB + d) * Q_BLK, &map_q, bar(0), d * 64, q0, head, pair, pl);
-            load_kv(&map_k, sK, bar(1), 0);
-            load_kv(&map_v, sV, bar(2), 0);
-            mbar_wait(bar(0), 0);
-            mbar_wait(bar(1), 0);
-            tc_fence_after();
-            mma_rows_x_rows<DH, PASSES>(tmem, sQ, Q_BLK, sK, KV_BLK);
-            umma_commit(bar(3));
+                    tma_load_5d(sQ + (pl * DB + d) * Q_BLK, &map_q, bar(B_Q), d * 64, q0, head, pair, pl);
+            load_kv(&map_k, sK, bar(B_K), 0);
+            if (nchunks > 1) load_kv(&map_k, sK + C::K_BUF, bar(B_K + 1), 1);
+            YV_AT(0);
+            mbar_wait(bar(B_Q), 0);
+            for (int c = 0; c < nchunks; ++c) {
+                const int b = c & 1;
+                const uint32_t use = (uint32_t)((c >> 1) & 1);              // parity of this buffer's (c / 2)-th use
+                if (c >= 1 && c + 1 < nchunks) {
+                    // prefetch chunk c + 1 into the other buffer as soon as S_{c-1} (its last reader) has retired, i.e.
+                    // BEFORE spending ~1.5k cycles on issuing S_c: the TMA latency hides behind the issue loop
+                    mbar_wait(bar(B_S + (b ^ 1)), (uint32_t)(((c - 1) >> 1) & 1));
+                    load_kv(&map_k, sK + (b ^ 1) * C::K_BUF, bar(B_K + (b ^ 1)), c + 1);
+                }
+                mbar_wait(bar(B_K + b), use);
+                if (c >= 2) mbar_wait(bar(B_SFREE + b), use ^ 1u);          // softmax has read S_{c-2} out of this buffer
+                YV_AT(8 + 8 * c + 0);
+                tc_fence_after();
+                mma_rows_x_rows<DH, PASSES>(tmem + (uint32_t)(b * KC), sQ, Q_BLK, sK + b * C::K_BUF, KV_BLK);
+                umma_commit(bar(B_S + b));
+                YV_AT(8 + 8 * c + 1);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ======================================= V loads, O += P V =======================================
+            load_kv(&map_v, sV, bar(B_V), 0);
             const uint32_t idesc_pv = make_idesc(QT, DH, 0, 1);
             for (int j = 0; j < nchunks; ++j) {
-                if (j + 1 < nchunks) {
-                    mbar_wait(bar(3 + (j & 1)), (uint32_t)((j >> 1) & 1));   // S_j retired: the K buffer is free
-                    load_kv(&map_k, sK, bar(1), j + 1);
-                    mbar_wait(bar(1), (uint32_t)((j + 1) & 1));
-                    tc_fence_after();
-                    mma_rows_x_rows<DH, PASSES>(tmem + (uint32_t)(((j + 1) & 1) * KC), sQ, Q_BLK, sK, KV_BLK);
-                    umma_commit(bar(3 + ((j + 1) & 1)));
-                }
-                mbar_wait(bar(5), (uint32_t)(j & 1));                        // P_j in shared memory, O rescaled
-                mbar_wait(bar(2), (uint32_t)(j & 1));                        // V_j landed
+                const uint32_t ph = (uint32_t)(j & 1);
+                mbar_wait(bar(B_P), ph);                                     // P_j in shared memory, O rescaled
+                YV_AT(8 + 8 * j + 2);
+                mbar_wait(bar(B_V), ph);                                     // V_j landed
                 tc_fence_after();
                 const int kc = min(KC, p.Tk - j * KC);
                 const int ksteps = (kc + 15) >> 4;
@@ -278,10 +336,11 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int s = 0; s < ksteps; ++s)
                     mma_terms<PASSES>(tmem_o, desc_k(sP, s), desc_k(sP + Q_BLK, s), desc_mn(sV, KV_BLK, s),
                                       desc_mn(sV + DB * KV_BLK, KV_BLK, s), idesc_pv, accum);
-                umma_commit(bar(6));
+                umma_commit(bar(B_O));
                 if (j + 1 < nchunks) {
-                    mbar_wait(bar(6), (uint32_t)(j & 1));                    // P V retired: V and P buffers are free
-                    load_kv(&map_v, sV, bar(2), j + 1);
+                    mbar_wait(bar(B_O), ph);                                 // P V retired: V and P buffers are free
+                    YV_AT(8 + 8 * j + 3);
+                    load_kv(&map_v, sV, bar(B_V), j + 1);
                 }
             }
         }
@@ -297,24 +356,30 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const float* mrow = p.mask ? p.mask + (long long)pair * p.Tk : nullptr;
         float m_ref = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nchunks; ++j) {
-            mbar_wait(bar(3 + (j & 1)), (uint32_t)((j >> 1) & 1));
+            const int key0 = j * KC + half * 32;
+            float x[32];
+            load_mask32(mrow, key0, p.Tk, x);
+            mbar_wait(bar(B_S + (j & 1)), (uint32_t)((j >> 1) & 1));
+            if (threadIdx.x == 0) YV_AT(8 + 8 * j + 4);
             tc_fence_after();
             uint32_t raw[32];
             tmem_ld32(tmem + lane_addr + (uint32_t)((j & 1) * KC + half * 32), raw);
-            const int key0 = j * KC + half * 32;
-            float x[32];
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_SFREE + (j & 1)));       // this S buffer may take chunk j + 2
+            if (threadIdx.x == 0) YV_AT(64 + 8 * j + 0);
             float mx = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int key = key0 + i;
-                x[i] = -INFINITY;
-                if (key < p.Tk) x[i] = __uint_as_float(raw[i]) * p.scale + (mrow ? __ldg(mrow + key) : 0.f);
+                x[i] = fmaf(__uint_as_float(raw[i]), p.scale, x[i]);      // -inf for keys past Tk
                 mx = fmaxf(mx, x[i]);
             }
             float* xmj = xm + (j & 1) * 2 * QT;
             xmj[half * QT + row] = mx;
+            if (threadIdx.x == 0) YV_AT(64 + 8 * j + 1);
             softmax_bar();
             mx = fmaxf(mx, xmj[(half ^ 1) * QT + row]);
+            if (threadIdx.x == 0) YV_AT(8 + 8 * j + 5);
             // online softmax with a lazy reference maximum: the accumulator is rescaled only when the row maximum
             // grew by more than RESCALE_THRESHOLD (both column halves take the same decision from the same numbers)
             const float m_new = (j == 0 || mx > m_ref + RESCALE_THRESHOLD) ? mx : m_ref;
@@ -331,8 +396,9 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                 for (int i = 0; i < 32; ++i) x[i] *= yv_drop_mul(drop, drop_row + (uint32_t)(key0 + i));
             }
+            if (threadIdx.x == 0) YV_AT(8 + 8 * j + 6);
             if (j > 0) {
-                mbar_wait(bar(6), (uint32_t)((j - 1) & 1));   // P V of the previous chunk retired
+                mbar_wait(bar(B_O), (uint32_t)((j - 1) & 1)); // P V of the previous chunk retired
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
@@ -346,14 +412,19 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     }
                 }
             }
+            if (threadIdx.x == 0) YV_AT(64 + 8 * j + 2);
             store_tile_row<PASSES>(sP, row, half, x);
+            if (threadIdx.x == 0) YV_AT(64 + 8 * j + 3);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(5));
+            if (lane == 0) mbar_arrive(bar(B_P));
+            if (threadIdx.x == 0) YV_AT(8 + 8 * j + 7);
         }
-        // ---- epilogue: O / l -> planes (+ fp32), log-sum-exp for the backward
-        mbar_wait(bar(6), (uint32_t)((nchunks - 1) & 1));
+        // ---- epilogue: O / l -> planes (+ fp32), log-sum-exp for the backward.  Every MMA has retired and no TMA load
+        // is in flight: the operand tiles are free and serve as the output staging area.
+        mbar_wait(bar(B_O), (uint32_t)((nchunks - 1) & 1));
+        if (threadIdx.x == 0) YV_AT(2);
         tc_fence_after();
         xl[half * QT + row] = l_run;
         softmax_bar();
@@ -365,21 +436,91 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             uint32_t o[32];
             const int col = half * (DH / 2) + g * 32;
             tmem_ld32(tmem_o + lane_addr + (uint32_t)col, o);
-            if (row_ok) {
-                float y[32];
+            float y[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]) * inv;
-                store_row32<PASSES>(p.o.ptr + grow * p.o.ld + head * DH + col, p.o.plane_stride,
-                                    p.o32 ? p.o32 + grow * p.o32_ld + head * DH + col : nullptr, y);
+            for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]) * inv;
+            stage_row32<DH>(tiles, row, col, y);
+            if (p.o32 && row_ok) {
+                float* dst32 = p.o32 + grow * p.o32_ld + head * DH + col;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(dst32 + 4 * i) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
             }
         }
         if (half == 0 && row_ok && p.lse) p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow] = m_ref + logf(l_tot);
+        softmax_bar();
+        copy_out_rows<DH>(tiles, p.o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
+        if (threadIdx.x == 0) YV_AT(3);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 8)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
+}
+
+// dK / dV planes of one (pair, head) = sum over the query tiles' slabs.  NS > 0: slab count known at compile time, all
+// NS * UNR loads of a batch are issued before the first add (the last CTA of a (pair, head) runs this alone).
+template <int DH, int NS>
+YV_DEVINL void sum_slabs(const AttnParams& p, int pair, int head, int nslabs) {
+    constexpr int V4 = DH / 4;
+    constexpr int UNR = NS == 1 ? 8 : 4;
+    const long long slab_stride = (long long)p.pairs * p.Tk * p.dkv_ld;
+    const int total = p.Tk * V4;
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+        const int col = t ? p.dv_col : p.dk_col;
+        const PlaneView& out = t ? p.dv : p.dk;
+#pragma unroll 1
+        for (int base = threadIdx.x; base < total; base += SM_THREADS * UNR) {
+            float4 acc[UNR];
+            if (NS > 0) {
+                float4 w[UNR][NS > 0 ? NS : 1];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int idx = min(base + u * SM_THREADS, total - 1);     // clamped: every load is unconditional
+                    const int key = idx / V4, c = (idx % V4) * 4;
+                    const float* src = p.dkv32 + ((long long)pair * p.Tk + key) * p.dkv_ld + col + head * DH + c;
+#pragma unroll
+                    for (int sl = 0; sl < (NS > 0 ? NS : 1); ++sl)
+                        w[u][sl] = __ldcg(reinterpret_cast<const float4*>(src + sl * slab_stride));
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    acc[u] = w[u][0];
+#pragma unroll
+                    for (int sl = 1; sl < (NS > 0 ? NS : 1); ++sl) {
+                        acc[u].x += w[u][sl].x; acc[u].y += w[u][sl].y; acc[u].z += w[u][sl].z; acc[u].w += w[u][sl].w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int idx = min(base + u * SM_THREADS, total - 1);
+                    const int key = idx / V4, c = (idx % V4) * 4;
+                    const float* src = p.dkv32 + ((long long)pair * p.Tk + key) * p.dkv_ld + col + head * DH + c;
+                    acc[u] = __ldcg(reinterpret_cast<const float4*>(src));
+                    for (int sl = 1; sl < nslabs; ++sl) {
+                        const float4 x = __ldcg(reinterpret_cast<const float4*>(src + sl * slab_stride));
+                        acc[u].x += x.x; acc[u].y += x.y; acc[u].z += x.z; acc[u].w += x.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int idx = base + u * SM_THREADS;
+                if (idx < total) {
+                    const int key = idx / V4, c = (idx % V4) * 4;
+                    uint32_t h0, l0, h1, l1;
+                    yv_split2(acc[u].x, acc[u].y, h0, l0);
+                    yv_split2(acc[u].z, acc[u].w, h1, l1);
+                    __nv_bfloat16* dst = out.ptr + ((long long)pair * p.Tk + key) * out.ld + head * DH + c;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(dst + out.plane_stride) = make_uint2(l0, l1);
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -392,39 +533,58 @@ struct BwdCfg {
     static constexpr uint32_t SDO = SQ + PL * DB * Q_BLK;
     static constexpr uint32_t SK = SDO + PL * DB * Q_BLK;
     static constexpr uint32_t SV = SK + PL * DB * KV_BLK;
-    static constexpr uint32_t ST = SV + PL * DB * KV_BLK;            // Pd, then dS
-    static constexpr uint32_t TILES = ST + PL * Q_BLK;
+    static constexpr uint32_t ST = SV + PL * DB * KV_BLK;            // Pd tile
+    // dS tile: V is dead once dPd = dO V^T has retired, so with 128-wide heads (where shared memory is full) the dS
+    // tile lives in the V buffer; 64-wide heads have room for a tile of their own
+    static constexpr uint32_t SD = DH == 128 ? SV : ST + PL * Q_BLK;
+    static constexpr uint32_t TILES = (DH == 128 ? ST : SD) + PL * Q_BLK;
     static constexpr uint32_t SMEM = HEADER + 1024 + TILES;
     static constexpr int TMEM_COLS = 512;   // S [0,64) dPd [64,128) dV^T [128,192) dK^T [192,256) dQ [256, 256 + DH)
+    static_assert(DH != 128 || PL * DB * KV_BLK == PL * Q_BLK, "dS tile must fit the V buffer");
     static_assert(SMEM <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+    static_assert(TILES >= 2u * QT * DH * 2, "the operand tiles double as the output staging area");
 };
 
-// rows of dO . O (the softmax-backward row term) for query row `grow`, from the global plane pairs
+// delta[r] = sum_d dO[r, d] * O[r, d] (the softmax-backward row term) for the 128 rows of a query tile, from the global
+// plane pairs: a warp reads whole rows (8 bytes per lane and plane, coalesced), four rows in flight, shuffle reduction
 template <int DH>
-YV_DEVINL float row_dot(const PlaneView& a, const PlaneView& b, long long grow, int head) {
-    const __nv_bfloat16* pa = a.ptr + grow * a.ld + head * DH;
-    const __nv_bfloat16* pb = b.ptr + grow * b.ld + head * DH;
-    float acc = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < DH; c += 8) {
-        const uint4 ah = *reinterpret_cast<const uint4*>(pa + c), al = *reinterpret_cast<const uint4*>(pa + a.plane_stride + c);
-        const uint4 bh = *reinterpret_cast<const uint4*>(pb + c), bl = *reinterpret_cast<const uint4*>(pb + b.plane_stride + c);
-        const uint32_t* ahp = reinterpret_cast<const uint32_t*>(&ah);
-        const uint32_t* alp = reinterpret_cast<const uint32_t*>(&al);
-        const uint32_t* bhp = reinterpret_cast<const uint32_t*>(&bh);
-        const uint32_t* blp = reinterpret_cast<const uint32_t*>(&bl);
+YV_DEVINL void row_dots(const PlaneView& a, const PlaneView& b, long long grow0, int rows_valid, int head, int warp, int lane,
+                        float* delta) {
+    constexpr int LPR = DH / 4;                 // lanes per row (4 bf16 = 8 bytes each)
+    constexpr int RPI = 32 / LPR;               // rows per warp instruction (1 for DH = 128, 2 for DH = 64)
+    const int c = (lane % LPR) * 4, rsub = lane / LPR;
+    for (int r0 = warp * RPI * 4; r0 < QT; r0 += 8 * RPI * 4) {
+        uint2 ah[4], al[4], bh[4], bl[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * RPI + rsub;
+            ah[u] = al[u] = bh[u] = bl[u] = make_uint2(0u, 0u);
+            if (r < rows_valid) {
+                const __nv_bfloat16* pa = a.ptr + (grow0 + r) * a.ld + head * DH + c;
+                const __nv_bfloat16* pb = b.ptr + (grow0 + r) * b.ld + head * DH + c;
+                ah[u] = __ldg(reinterpret_cast<const uint2*>(pa));
+                al[u] = __ldg(reinterpret_cast<const uint2*>(pa + a.plane_stride));
+                bh[u] = __ldg(reinterpret_cast<const uint2*>(pb));
+                bl[u] = __ldg(reinterpret_cast<const uint2*>(pb + b.plane_stride));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
             // bf16 -> fp32 is a 16-bit shift
-            const float a0 = __uint_as_float(ahp[e] << 16) + __uint_as_float(alp[e] << 16);
-            const float a1 = __uint_as_float(ahp[e] & 0xffff0000u) + __uint_as_float(alp[e] & 0xffff0000u);
-            const float b0 = __uint_as_float(bhp[e] << 16) + __uint_as_float(blp[e] << 16);
-            const float b1 = __uint_as_float(bhp[e] & 0xffff0000u) + __uint_as_float(blp[e] & 0xffff0000u);
-            acc = fmaf(a0, b0, acc);
-            acc = fmaf(a1, b1, acc);
+            const float a0 = __uint_as_float(ah[u].x << 16) + __uint_as_float(al[u].x << 16);
+            const float a1 = __uint_as_float(ah[u].x & 0xffff0000u) + __uint_as_float(al[u].x & 0xffff0000u);
+            const float a2 = __uint_as_float(ah[u].y << 16) + __uint_as_float(al[u].y << 16);
+            const float a3 = __uint_as_float(ah[u].y & 0xffff0000u) + __uint_as_float(al[u].y & 0xffff0000u);
+            const float b0 = __uint_as_float(bh[u].x << 16) + __uint_as_float(bl[u].x << 16);
+            const float b1 = __uint_as_float(bh[u].x & 0xffff0000u) + __uint_as_float(bl[u].x & 0xffff0000u);
+            const float b2 = __uint_as_float(bh[u].y << 16) + __uint_as_float(bl[u].y << 16);
+            const float b3 = __uint_as_float(bh[u].y & 0xffff0000u) + __uint_as_float(bl[u].y & 0xffff0000u);
+            float acc = fmaf(a0, b0, fmaf(a1, b1, fmaf(a2, b2, a3 * b3)));
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((lane % LPR) == 0) delta[r0 + u * RPI + rsub] = acc;
         }
     }
-    return acc;
 }
 
 template <int DH, int PASSES>
@@ -435,11 +595,16 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     using C = BwdCfg<DH, PASSES>;
     constexpr int PL = C::PL, DB = C::DB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);         // 0 Q+dO, 1 K+V, 2 S+dPd, 3 Pd, 4 dV, 5 dS, 6 dK+dQ
+    // barriers: 0 Q+dO landed, 1 K+V landed, 2 S retired, 3 dPd retired, 4 Pd+dS tiles written, 5 dV^T retired,
+    //           6 dK^T+dQ retired
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 64);
     uint32_t* last_flag = reinterpret_cast<uint32_t*>(smem_raw + 68);
+    float* delta_s = reinterpret_cast<float*>(smem_raw + 256);      // [128] row terms dO . O
+    constexpr int B_QDO = 0, B_KV = 1, B_S = 2, B_DP = 3, B_T = 4, B_DV = 5, B_DKQ = 6;
     const uint32_t tiles = (smem_u32(smem_raw) + C::HEADER + 1023u) & ~1023u;
-    const uint32_t sQ = tiles + C::SQ, sDO = tiles + C::SDO, sK = tiles + C::SK, sV = tiles + C::SV, sT = tiles + C::ST;
+    const uint32_t sQ = tiles + C::SQ, sDO = tiles + C::SDO, sK = tiles + C::SK, sV = tiles + C::SV, sT = tiles + C::ST,
+                   sD = tiles + C::SD;
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * i; };
 
@@ -450,13 +615,13 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     yv_pdl_trigger();
 
     if (threadIdx.x == 0) {
-        mbar_init(bar(0), 1);
-        mbar_init(bar(1), 1);
-        mbar_init(bar(2), 1);
-        mbar_init(bar(3), 8);
-        mbar_init(bar(4), 1);
-        mbar_init(bar(5), 8);
-        mbar_init(bar(6), 1);
+        mbar_init(bar(B_QDO), 1);
+        mbar_init(bar(B_KV), 1);
+        mbar_init(bar(B_S), 1);
+        mbar_init(bar(B_DP), 1);
+        mbar_init(bar(B_T), 8);
+        mbar_init(bar(B_DV), 1);
+        mbar_init(bar(B_DKQ), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_k) : "memory");
@@ -476,9 +641,10 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const uint32_t tm_s = tmem, tm_dp = tmem + 64, tm_dv = tmem + 128, tm_dk = tmem + 192, tm_dq = tmem + 256;
     yv_pdl_wait();
 
+    const uint32_t idesc_t = make_idesc(128, KC, 1, 1);          // dV^T / dK^T: both operands MN-major
     if (warp == 8) {
         if (lane == 0) {
-            // ===================================== TMA + MMA issue =====================================
+            // =========================== loads, S = Q K^T, dV^T = dO^T Pd ===========================
             auto load_rows = [&](const CUtensorMap* map, uint32_t dst, uint32_t blk, uint32_t b, int row0) {
 #pragma unroll
                 for (int pl = 0; pl < PL; ++pl)
@@ -486,23 +652,24 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     for (int d = 0; d < DB; ++d)
                         tma_load_5d(dst + (pl * DB + d) * blk, map, b, d * 64, row0, head, pair, pl);
             };
-            mbar_expect_tx(bar(0), 2 * PL * DB * Q_BLK);
-            load_rows(&map_q, sQ, Q_BLK, bar(0), q0);
-            load_rows(&map_do, sDO, Q_BLK, bar(0), q0);
-            mbar_expect_tx(bar(1), 2 * PL * DB * KV_BLK);
-            load_rows(&map_k, sK, KV_BLK, bar(1), 0);
-            load_rows(&map_v, sV, KV_BLK, bar(1), 0);
-            mbar_wait(bar(0), 0);
-            const uint32_t idesc_t = make_idesc(128, KC, 1, 1);          // dV^T / dK^T: both operands MN-major
-            const uint32_t idesc_dq = make_idesc(QT, DH, 0, 1);
+            YV_AT(0);
+            mbar_expect_tx(bar(B_QDO), 2 * PL * DB * Q_BLK);
+            load_rows(&map_q, sQ, Q_BLK, bar(B_QDO), q0);
+            load_rows(&map_do, sDO, Q_BLK, bar(B_QDO), q0);
+            mbar_expect_tx(bar(B_KV), 2 * PL * DB * KV_BLK);
+            load_rows(&map_k, sK, KV_BLK, bar(B_KV), 0);
+            load_rows(&map_v, sV, KV_BLK, bar(B_KV), 0);
+            mbar_wait(bar(B_QDO), 0);
             for (int j = 0; j < nchunks; ++j) {
                 const uint32_t ph = (uint32_t)(j & 1);
-                mbar_wait(bar(1), ph);
+                mbar_wait(bar(B_KV), ph);
+                YV_AT(8 + 16 * j + 0);
                 tc_fence_after();
-                mma_rows_x_rows<DH, PASSES>(tm_s, sQ, Q_BLK, sK, KV_BLK);      // S   = Q  K^T
-                mma_rows_x_rows<DH, PASSES>(tm_dp, sDO, Q_BLK, sV, KV_BLK);    // dPd = dO V^T
-                umma_commit(bar(2));
-                mbar_wait(bar(3), ph);                                          // Pd tile written
+                mma_rows_x_rows<DH, PASSES>(tm_s, sQ, Q_BLK, sK, KV_BLK);
+                umma_commit(bar(B_S));
+                YV_AT(8 + 16 * j + 1);
+                mbar_wait(bar(B_T), ph);                                        // Pd and dS tiles written
+                YV_AT(8 + 16 * j + 2);
                 tc_fence_after();
                 {   // dV^T [DH x 64] = dO^T . Pd : contraction over the 128 query rows
                     uint32_t accum = 0;
@@ -511,31 +678,49 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         mma_terms<PASSES>(tm_dv, desc_mn(sDO, Q_BLK, s), desc_mn(sDO + DB * Q_BLK, Q_BLK, s),
                                           desc_mn(sT, Q_BLK, s), desc_mn(sT + Q_BLK, Q_BLK, s), idesc_t, accum);
                 }
-                umma_commit(bar(4));
-                mbar_wait(bar(5), ph);                                          // dS tile written (dV^T retired before)
+                umma_commit(bar(B_DV));
+                YV_AT(8 + 16 * j + 3);
+                if (j + 1 < nchunks) {
+                    mbar_wait(bar(B_DV), ph);                                   // Pd tile consumed
+                    mbar_wait(bar(B_DKQ), ph);                                  // K and V (= dS tile) consumed
+                    YV_AT(8 + 16 * j + 4);
+                    mbar_expect_tx(bar(B_KV), 2 * PL * DB * KV_BLK);
+                    load_rows(&map_k, sK, KV_BLK, bar(B_KV), (j + 1) * KC);
+                    load_rows(&map_v, sV, KV_BLK, bar(B_KV), (j + 1) * KC);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // =========================== dPd = dO V^T, dK^T = Q^T dS, dQ += dS K ===========================
+            const uint32_t idesc_dq = make_idesc(QT, DH, 0, 1);
+            mbar_wait(bar(B_QDO), 0);
+            for (int j = 0; j < nchunks; ++j) {
+                const uint32_t ph = (uint32_t)(j & 1);
+                mbar_wait(bar(B_KV), ph);
+                tc_fence_after();
+                mma_rows_x_rows<DH, PASSES>(tm_dp, sDO, Q_BLK, sV, KV_BLK);
+                umma_commit(bar(B_DP));
+                YV_AT(8 + 16 * j + 5);
+                mbar_wait(bar(B_T), ph);
                 tc_fence_after();
                 {   // dK^T [DH x 64] = Q^T . dS
                     uint32_t accum = 0;
 #pragma unroll
                     for (int s = 0; s < 8; ++s)
                         mma_terms<PASSES>(tm_dk, desc_mn(sQ, Q_BLK, s), desc_mn(sQ + DB * Q_BLK, Q_BLK, s),
-                                          desc_mn(sT, Q_BLK, s), desc_mn(sT + Q_BLK, Q_BLK, s), idesc_t, accum);
+                                          desc_mn(sD, Q_BLK, s), desc_mn(sD + Q_BLK, Q_BLK, s), idesc_t, accum);
                 }
                 {   // dQ [128 x DH] += dS . K : contraction over the keys of this chunk
                     const int kc = min(KC, p.Tk - j * KC);
                     const int ksteps = (kc + 15) >> 4;
                     uint32_t accum = j > 0 ? 1u : 0u;
                     for (int s = 0; s < ksteps; ++s)
-                        mma_terms<PASSES>(tm_dq, desc_k(sT, s), desc_k(sT + Q_BLK, s), desc_mn(sK, KV_BLK, s),
+                        mma_terms<PASSES>(tm_dq, desc_k(sD, s), desc_k(sD + Q_BLK, s), desc_mn(sK, KV_BLK, s),
                                           desc_mn(sK + DB * KV_BLK, KV_BLK, s), idesc_dq, accum);
                 }
-                umma_commit(bar(6));
-                if (j + 1 < nchunks) {
-                    mbar_wait(bar(6), ph);                                      // K, V and the dS tile are free
-                    mbar_expect_tx(bar(1), 2 * PL * DB * KV_BLK);
-                    load_rows(&map_k, sK, KV_BLK, bar(1), (j + 1) * KC);
-                    load_rows(&map_v, sV, KV_BLK, bar(1), (j + 1) * KC);
-                }
+                umma_commit(bar(B_DKQ));
+                YV_AT(8 + 16 * j + 6);
             }
         }
     } else {
@@ -550,30 +735,29 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const float* mrow = p.mask ? p.mask + (long long)pair * p.Tk : nullptr;
         const long long grow = (long long)pair * p.Tq + qrow;
         // rows past Tq (zero-filled by TMA) get lse = +inf: their probabilities and dS are exactly zero
-        float lse = INFINITY, delta = 0.f;
-        if (row_ok) {
-            lse = p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow];
-            delta = row_dot<DH>(p.d_o, p.fwd_o, grow, head);
-        }
-        const int d_lane = quarter * 32 + lane;                     // TMEM lane of dV^T / dK^T = head dimension index
-        float* dkv_base = p.dkv32 + (long long)pair * p.Tk * p.dkv_ld + head * DH + d_lane;
+        row_dots<DH>(p.d_o, p.fwd_o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane, delta_s);
+        const float lse = row_ok ? p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow] : INFINITY;
+        softmax_bar();
+        const float delta = delta_s[row];
+        // partial dK / dV of this query tile: slab `qtile` of the workspace, lane = head dimension index
+        const int d_lane = quarter * 32 + lane;
+        float* slab = p.dkv32 + ((long long)qtile * p.pairs + pair) * p.Tk * p.dkv_ld + head * DH + d_lane;
         for (int j = 0; j < nchunks; ++j) {
             const uint32_t ph = (uint32_t)(j & 1);
             const int key0 = j * KC + half * 32;
-            mbar_wait(bar(2), ph);
-            tc_fence_after();
             float pd[32], ds[32];
+            load_mask32(mrow, key0, p.Tk, pd);
+            mbar_wait(bar(B_S), ph);
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 8);
+            tc_fence_after();
             {
                 uint32_t raw[32];
                 tmem_ld32(tm_s + lane_addr + (uint32_t)(half * 32), raw);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + i;
-                    float pr = 0.f;
-                    if (key < p.Tk)
-                        pr = __expf(__uint_as_float(raw[i]) * p.scale + (mrow ? __ldg(mrow + key) : 0.f) - lse);
-                    pd[i] = pr;
-                }
+                for (int i = 0; i < 32; ++i)
+                    pd[i] = __expf(fmaf(__uint_as_float(raw[i]), p.scale, pd[i]) - lse);   // 0 past Tk / past Tq
+                mbar_wait(bar(B_DP), ph);
+                tc_fence_after();
                 tmem_ld32(tm_dp + lane_addr + (uint32_t)(half * 32), raw);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -583,79 +767,89 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     pd[i] = pr * mult;
                 }
             }
-            if (j > 0) mbar_wait(bar(6), (uint32_t)((j - 1) & 1));   // previous dK^T / dQ products retired: tile is free
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 9);
+            // (the products that read the previous chunk's tiles retired before this thread drained their results)
             store_tile_row<PASSES>(sT, row, half, pd);
+            store_tile_row<PASSES>(sD, row, half, ds);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(3));
-            mbar_wait(bar(4), ph);                                    // dV^T complete, the Pd tile has been consumed
+            if (lane == 0) mbar_arrive(bar(B_T));
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 10);
+            // drain dV^T and dK^T (lane = d, column = key): 128-byte coalesced rows of the slab
+            const int nkeys = min(32, p.Tk - key0);               // warp-uniform
+            mbar_wait(bar(B_DV), ph);
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 11);
             tc_fence_after();
-            store_tile_row<PASSES>(sT, row, half, ds);
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(5));
-            // drain dV^T (lane = d, column = key) into the fp32 scratch while dK^T / dQ run
             if (DH == 128 || quarter < 2) {
                 uint32_t raw[32];
                 tmem_ld32(tm_dv + lane_addr + (uint32_t)(half * 32), raw);
+                float* dst = slab + (long long)key0 * p.dkv_ld + p.dv_col;
+                if (nkeys >= 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (key0 + i < p.Tk)
-                        atomicAdd(dkv_base + (long long)(key0 + i) * p.dkv_ld + p.dv_col, __uint_as_float(raw[i]));
+                    for (int i = 0; i < 32; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nkeys) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                }
             }
-            mbar_wait(bar(6), ph);
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 12);
+            mbar_wait(bar(B_DKQ), ph);
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 13);
             tc_fence_after();
             if (DH == 128 || quarter < 2) {
                 uint32_t raw[32];
                 tmem_ld32(tm_dk + lane_addr + (uint32_t)(half * 32), raw);
+                float* dst = slab + (long long)key0 * p.dkv_ld + p.dk_col;
+                if (nkeys >= 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (key0 + i < p.Tk)
-                        atomicAdd(dkv_base + (long long)(key0 + i) * p.dkv_ld + p.dk_col, __uint_as_float(raw[i]));
+                    for (int i = 0; i < 32; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nkeys) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                }
             }
             tc_fence_before();
+            if (threadIdx.x == 0) YV_AT(8 + 16 * j + 14);
         }
-        // ---- dQ tile -> planes
+        if (threadIdx.x == 0) YV_AT(1);
+        // ---- dQ tile -> planes through the (now free) operand tiles
 #pragma unroll 1
         for (int g = 0; g < DH / 64; ++g) {
             uint32_t o[32];
             const int col = half * (DH / 2) + g * 32;
             tmem_ld32(tm_dq + lane_addr + (uint32_t)col, o);
-            if (row_ok) {
-                float y[32];
+            float y[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]);
-                store_row32<PASSES>(p.dq.ptr + grow * p.dq.ld + head * DH + col, p.dq.plane_stride, nullptr, y);
-            }
+            for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]);
+            stage_row32<DH>(tiles, row, col, y);
         }
-        // ---- the last query tile of this (pair, head) converts the reduced dK / dV to planes
-        __threadfence();
+        __threadfence();                                      // this tile's slab is visible before the ticket is taken
         softmax_bar();
-        if (threadIdx.x == 0) *last_flag = (atomicAdd(p.tickets + pair * p.heads + head, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (threadIdx.x == 0) YV_AT(2);
+        copy_out_rows<DH>(tiles, p.dq, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
+        // ---- the last query tile of this (pair, head) adds the slabs and writes the dK / dV planes
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(p.tickets + pair * p.heads + head, 1u);
+            const bool last = t == gridDim.x - 1;
+            if (last) p.tickets[pair * p.heads + head] = 0u;  // self-resetting: the buffer can be reused by the next launch
+            *last_flag = last ? 1u : 0u;
+        }
         softmax_bar();
+        if (threadIdx.x == 0) YV_AT(3);
         if (*last_flag) {
             __threadfence();
-            constexpr int V4 = DH / 4;
-            for (int idx = threadIdx.x; idx < p.Tk * V4; idx += SM_THREADS) {
-                const int key = idx / V4, c = (idx % V4) * 4;
-                const long long krow = (long long)pair * p.Tk + key;
-                const float* src = p.dkv32 + krow * p.dkv_ld + head * DH + c;
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (t ? p.dv_col : p.dk_col)));
-                    const PlaneView& out = t ? p.dv : p.dk;
-                    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-                    yv_split(v.x, h0, l0); yv_split(v.y, h1, l1); yv_split(v.z, h2, l2); yv_split(v.w, h3, l3);
-                    __nv_bfloat16* dst = out.ptr + krow * out.ld + head * DH + c;
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-                    *reinterpret_cast<uint2*>(dst + out.plane_stride) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
-                }
-            }
+            const int nslabs = (int)gridDim.x;
+            if (nslabs == 1) sum_slabs<DH, 1>(p, pair, head, 1);
+            else if (nslabs == 2) sum_slabs<DH, 2>(p, pair, head, 2);
+            else if (nslabs == 3) sum_slabs<DH, 3>(p, pair, head, 3);
+            else sum_slabs<DH, 0>(p, pair, head, nslabs);
         }
     }
 
+    if (threadIdx.x == 0) YV_AT(4);
     tc_fence_before();
     __syncthreads();
     if (warp == 8)
@@ -687,15 +881,16 @@ PlaneView plane_view(const YvHeadView& v) {
     return r;
 }
 
-// per-device one-time opt-in to > 48 KB of dynamic shared memory (cudaFuncSetAttribute is per device)
+// per-device one-time opt-in to > 48 KB of dynamic shared memory (cudaFuncSetAttribute is a per-device setting and the
+// reference's nn.DataParallel fallback calls forward from one host thread per device)
 template <typename K>
-int set_smem_once(K kernel, int bytes, unsigned long long* done_mask) {
+int set_smem_once(K kernel, int bytes, bool (&done)[64], std::mutex& mu) {
     int dev = 0;
     YV_CUDA(cudaGetDevice(&dev));
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev & 63]) return 0;
     YV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+    done[dev & 63] = true;
     return 0;
 }
 
@@ -706,8 +901,9 @@ int launch_fwd(const YvAttnFwd* a, const AttnParams& p, cudaStream_t st) {
     if (view_map(&mq, a->q, a->pairs, a->heads, DH, PASSES, QT, "Q")) return 1;
     if (view_map(&mk, a->k, a->pairs, a->heads, DH, PASSES, KC, "K")) return 1;
     if (view_map(&mv, a->v, a->pairs, a->heads, DH, PASSES, KC, "V")) return 1;
-    static unsigned long long done = 0;
-    if (set_smem_once(yv_attn_fwd_kernel<DH, PASSES>, (int)C::SMEM, &done)) return 2;
+    static bool done[64] = {};
+    static std::mutex mu;
+    if (set_smem_once(yv_attn_fwd_kernel<DH, PASSES>, (int)C::SMEM, done, mu)) return 2;
     dim3 grid((unsigned)((p.Tq + QT - 1) / QT), (unsigned)a->heads, (unsigned)a->pairs);
     YV_CUDA(yv_launch(yv_attn_fwd_kernel<DH, PASSES>, grid, dim3(ATT_THREADS), C::SMEM, st, mq, mk, mv, p));
     return 0;
@@ -721,8 +917,9 @@ int launch_bwd(const YvAttnBwd* a, const AttnParams& p, cudaStream_t st) {
     if (view_map(&mk, a->k, a->pairs, a->heads, DH, PASSES, KC, "K")) return 1;
     if (view_map(&mv, a->v, a->pairs, a->heads, DH, PASSES, KC, "V")) return 1;
     if (view_map(&md, a->dout, a->pairs, a->heads, DH, PASSES, QT, "dO")) return 1;
-    static unsigned long long done = 0;
-    if (set_smem_once(yv_attn_bwd_kernel<DH, PASSES>, (int)C::SMEM, &done)) return 2;
+    static bool done[64] = {};
+    static std::mutex mu;
+    if (set_smem_once(yv_attn_bwd_kernel<DH, PASSES>, (int)C::SMEM, done, mu)) return 2;
     dim3 grid((unsigned)((p.Tq + QT - 1) / QT), (unsigned)a->heads, (unsigned)a->pairs);
     YV_CUDA(yv_launch(yv_attn_bwd_kernel<DH, PASSES>, grid, dim3(ATT_THREADS), C::SMEM, st, mq, mk, mv, md, p));
     return 0;
@@ -779,10 +976,10 @@ extern "C" int yv_attn_fwd(const YvAttnFwd* a, yv_stream_t stream) {
     return 0;
 }
 
-extern "C" size_t yv_attn_bwd_workspace_bytes(int32_t pairs, int32_t heads, int32_t dh, int32_t Tk) {
-    if (pairs <= 0 || heads <= 0 || dh <= 0 || Tk <= 0) return 0;
-    // fp32 [pairs * Tk, 2 * heads * dh] (dK | dV) followed by one ticket per (pair, head)
-    return (size_t)pairs * Tk * 2 * heads * dh * sizeof(float) + (size_t)pairs * heads * sizeof(uint32_t);
+extern "C" size_t yv_attn_bwd_workspace_bytes(int32_t pairs, int32_t heads, int32_t dh, int32_t Tq, int32_t Tk) {
+    if (pairs <= 0 || heads <= 0 || dh <= 0 || Tq <= 0 || Tk <= 0) return 0;
+    // one fp32 slab [pairs * Tk, 2 * heads * dh] (dK | dV) per 128-query tile
+    return (size_t)((Tq + QT - 1) / QT) * pairs * Tk * 2 * heads * dh * sizeof(float);
 }
 
 extern "C" int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream) {
@@ -800,9 +997,10 @@ extern "C" int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream) {
         check_view(a->out, a->heads, a->dh, "O") || check_view(a->dq, a->heads, a->dh, "dQ") ||
         check_view(a->dk, a->heads, a->dh, "dK") || check_view(a->dv, a->heads, a->dh, "dV"))
         return 1;
-    const size_t need = yv_attn_bwd_workspace_bytes(a->pairs, a->heads, a->dh, a->k.rows);
+    const size_t need = yv_attn_bwd_workspace_bytes(a->pairs, a->heads, a->dh, a->q.rows, a->k.rows);
     YV_CHECK(a->workspace != nullptr && a->workspace_bytes >= need && ((uintptr_t)a->workspace & 15) == 0,
-             "yv_attn_bwd: workspace of %zu zero-filled bytes required (got %zu)", need, (size_t)a->workspace_bytes);
+             "yv_attn_bwd: workspace of %zu bytes required (got %zu)", need, (size_t)a->workspace_bytes);
+    YV_CHECK(a->tickets != nullptr, "yv_attn_bwd: tickets (pairs*heads zero-initialised uint32) required");
     if (get_encode()) return 1;
     const int H = a->heads * a->dh;
     AttnParams p = {};
@@ -818,8 +1016,7 @@ extern "C" int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream) {
     p.dkv32 = reinterpret_cast<float*>(a->workspace);
     p.dkv_ld = 2 * H;
     p.dk_col = 0; p.dv_col = H;
-    p.tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a->workspace) +
-                                            (size_t)a->pairs * a->k.rows * 2 * H * sizeof(float));
+    p.tickets = a->tickets;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;
     if (a->dh == 128) rc = a->passes == 3 ? launch_bwd<128, 3>(a, p, st) : launch_bwd<128, 1>(a, p, st);

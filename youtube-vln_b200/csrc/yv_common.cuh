@@ -62,11 +62,30 @@ YV_DEVINL YvDrop yv_drop_make(const unsigned long long* rng, uint32_t site, floa
     return d;
 }
 
-// multiplier applied to element `idx`: 0 (dropped) or 1/(1-p) (kept)
+// multiplier applied to element `idx`: 0 (dropped) or 1/(1-p) (kept).  One avalanche round keyed twice: the site key
+// enters before the first multiply, the step key between the two multiplies (10 integer ops per element; the fused
+// attention kernels hash every probability twice per step, forward and backward).
+YV_DEVINL uint32_t yv_drop_hash(const YvDrop& d, uint32_t idx) {
+    uint32_t x = idx ^ d.k0;
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x += d.k1;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
 YV_DEVINL float yv_drop_mul(const YvDrop& d, uint32_t idx) {
     if (d.thresh == 0) return 1.f;
-    uint32_t h = yv_mix32(yv_mix32(idx ^ d.k0) + d.k1);
-    return h >= d.thresh ? d.scale : 0.f;
+    return yv_drop_hash(d, idx) >= d.thresh ? d.scale : 0.f;
+}
+
+// two fp32 values -> packed bf16x2 hi and lo words (element a in the low half): x ~= hi + lo
+YV_DEVINL void yv_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -275,6 +275,13 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+struct DevCache {
+    int num_sms = 0;
+    bool attr_set = false;
+};
+DevCache g_dev_cache[64];
+std::mutex g_dev_mutex;
+
 }  // namespace
 
 void yv_count_launch();
@@ -337,22 +344,26 @@ extern "C" int YV_GEMM_ENTRY(const YvGemm* g, yv_stream_t stream) {
     const long long total_tiles = (long long)tiles * a.nb0 * a.nb1 * p.splits;
     YV_CHECK(total_tiles < 2147483647LL, "yv_gemm: too many tiles");
     p.total_tiles = (int)total_tiles;
-    static int num_sms = 0;
-    if (num_sms == 0) {
+    // per-device cache behind a mutex: the reference's nn.DataParallel fallback (utils/distributed.py:100-102) calls
+    // forward from one thread per device, and cudaFuncSetAttribute is a per-device setting
+    int num_sms = 0;
+    {
         int dev = 0;
         YV_CUDA(cudaGetDevice(&dev));
-        YV_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        DevCache& dc = g_dev_cache[dev & 63];
+        if (dc.num_sms == 0) YV_CUDA(cudaDeviceGetAttribute(&dc.num_sms, cudaDevAttrMultiProcessorCount, dev));
+        if (!dc.attr_set) {
+            YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+            YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
+            dc.attr_set = true;
+        }
+        num_sms = dc.num_sms;
     }
     dim3 grid((unsigned)((!PERSISTENT || total_tiles < num_sms) ? total_tiles : num_sms), 1, 1);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p.splits > 1 && !g->out32_zeroed)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
-        attr_set = true;
-    }
     if (g->passes == 3)
         YV_CUDA(yv_launch(yv_gemm_kernel<3>, grid, dim3(NUM_THREADS), Cfg<3>::SMEM_BYTES, st, ma, mb, p));
     else

@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/yvb200.h"
 #include "yv_common.cuh"
 

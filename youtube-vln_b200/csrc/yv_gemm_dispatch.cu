@@ -3,6 +3,8 @@
 //   yv_gemm_pair (yv_gemm_pair.cu)           two CTAs per 256 x {128,256} tile (cta_group::2)
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "../../include/yvb200.h"
 #include "yv_common.cuh"
 
@@ -16,19 +18,19 @@ extern "C" int yv_gemm_pair_splits(const YvGemm* g, int pair_n);
 namespace {
 // 0 = automatic; 32 / 64 = the single-CTA variants; 2 = CTA pairs (tile width chosen per problem);
 // 128 / 256 = CTA pairs with that tile width.  Initial value from YVB200_GEMM_VARIANT.
-int g_variant = []() { const char* e = getenv("YVB200_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
+std::atomic<int> g_variant{[]() { const char* e = getenv("YVB200_GEMM_VARIANT"); return e ? atoi(e) : 0; }()};
 }  // namespace
 
 extern "C" int yv_gemm_set_variant(int variant) {
     YV_CHECK(variant == 0 || variant == 32 || variant == 64 || variant == 2 || variant == 128 || variant == 256,
              "yv_gemm_set_variant: unknown variant %d", variant);
-    g_variant = variant;
+    g_variant.store(variant);
     return 0;
 }
 
 extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
     YV_CHECK(g != nullptr, "yv_gemm: NULL args");
-    const int force = g_variant;
+    const int force = g_variant.load(std::memory_order_relaxed);
     if (force == 32) return yv_gemm_k32(g, stream);
     if (force == 64) return yv_gemm_k64(g, stream);
     if (force == 2) return yv_gemm_pair(g, 0, stream);
@@ -47,7 +49,7 @@ extern "C" int yv_gemm(const YvGemm* g, yv_stream_t stream) {
 // saves the memset node in front of the kernel.
 extern "C" int yv_gemm_splits(const YvGemm* g) {
     if (g == nullptr || g->M <= 0 || g->N <= 0 || g->K <= 0) return 1;
-    const int force = g_variant;
+    const int force = g_variant.load(std::memory_order_relaxed);
     if (force == 32) return yv_gemm_k32_splits(g);
     if (force == 2) return yv_gemm_pair_splits(g, 0);
     if (force == 128 || force == 256) return yv_gemm_pair_splits(g, force);

@@ -349,11 +349,17 @@ extern "C" int yv_gemm_pair(const YvGemm* g, int pair_n, yv_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p.splits > 1 && !g->out32_zeroed)
         YV_CUDA(cudaMemset2DAsync(g->out32, sizeof(float) * g->ld_out, 0, sizeof(float) * g->N, g->M, st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        attr_set = true;
+    {   // per device, behind a mutex (one host thread per device under nn.DataParallel)
+        static bool attr_set[64] = {};
+        static std::mutex mu;
+        int dev = 0;
+        YV_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (!attr_set[dev & 63]) {
+            YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+            YV_CUDA(cudaFuncSetAttribute(yv_gemm_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+            attr_set[dev & 63] = true;
+        }
     }
     if (g->passes == 3)
         YV_CUDA(yv_launch(yv_gemm_pair_kernel<3>, grid, dim3(NUM_THREADS), PCfg<3>::smem_bytes(p.stages, pair_n), st, ma, mb, p));

@@ -933,6 +933,7 @@ ce_loss_kernel(const float* __restrict__ logits, long long ld, const long long* 
     const long long row = blockIdx.x;
     const long long t = target[row];
     if (t < 0) return;
+    if (t >= cols) __trap();           // label outside the vocabulary (ATen raises a device assert here too)
     const float* lr = logits + row * ld;
     float mx = -INFINITY;
     for (int c = threadIdx.x; c < cols; c += THREADS) mx = fmaxf(mx, lr[c]);
@@ -955,6 +956,7 @@ ce_grad_kernel(const float* __restrict__ logits, long long ld, const long long* 
     __shared__ float sh[WARPS];
     const long long row = blockIdx.x;
     const long long t = target[row];
+    if (t >= cols) __trap();
     const float* lr = logits + row * ld;
     float mx = 0.f, inv = 0.f, g = 0.f;
     if (t >= 0) {

@@ -864,8 +864,14 @@ class BertModel(BertPreTrainedModel):
         if image_attention_mask is None:
             image_attention_mask = torch.ones(input_imgs.size(0), input_imgs.size(1)).type_as(input_txt)
         if input_imgs.is_cuda:
-            # one launch converts every stale weight of this process to bf16 hi/lo planes
-            _cuda_ops(input_imgs).rt(input_imgs.device).arena.refresh_all()
+            r = _cuda_ops(input_imgs).rt(input_imgs.device)
+            # one launch per arena chunk converts the weights to bf16 hi/lo planes.  While training (or whenever autograd
+            # is on) every weight is converted: the reference's optimizer updates ``p.data`` in place, which the
+            # version counters cannot see.  Pure inference only converts what changed.
+            r.arena.refresh_for_forward(force=self.training or torch.is_grad_enabled())
+            if self.training:
+                # fresh dropout masks for this forward (its backward regenerates them from the same snapshot)
+                r.begin_training_forward()
         # additive masks: 0 where attended, -10000 where padded (reference :1268-1287)
         ext_t = (1.0 - attention_mask.unsqueeze(1).unsqueeze(2).to(dtype=torch.float32)) * -10000.0
         ext_v = (1.0 - image_attention_mask.unsqueeze(1).unsqueeze(2).to(dtype=torch.float32)) * -10000.0

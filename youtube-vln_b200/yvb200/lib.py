@@ -66,7 +66,7 @@ class YvAttnBwd(C.Structure):
                 ("mask", C.c_void_p), ("scale", C.c_float), ("drop_p", C.c_float), ("drop_site", C.c_uint32),
                 ("_pad", C.c_uint32), ("rng", C.c_void_p), ("lse", C.c_void_p),
                 ("dq", YvHeadView), ("dk", YvHeadView), ("dv", YvHeadView),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("tickets", C.c_void_p)]
 
 
 class YvSplitSeg(C.Structure):
@@ -394,8 +394,9 @@ def attn_supported(dh: int, passes: int) -> bool:
     return bool(load().yv_attn_supported(C.c_int32(dh), C.c_int32(passes)))
 
 
-def attn_bwd_workspace_bytes(pairs: int, heads: int, dh: int, Tk: int) -> int:
-    return int(load().yv_attn_bwd_workspace_bytes(C.c_int32(pairs), C.c_int32(heads), C.c_int32(dh), C.c_int32(Tk)))
+def attn_bwd_workspace_bytes(pairs: int, heads: int, dh: int, Tq: int, Tk: int) -> int:
+    return int(load().yv_attn_bwd_workspace_bytes(C.c_int32(pairs), C.c_int32(heads), C.c_int32(dh), C.c_int32(Tq),
+                                                  C.c_int32(Tk)))
 
 
 def attn_fwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, mask, pairs: int, heads: int, dh: int, scale: float,
@@ -413,9 +414,9 @@ def attn_fwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, mask, pairs: int, head
 
 def attn_bwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, dout: YvHeadView, out: YvHeadView, mask, lse, pairs: int,
              heads: int, dh: int, scale: float, dq: YvHeadView, dk: YvHeadView, dv: YvHeadView, workspace: torch.Tensor,
-             passes: int = 3, drop_p: float = 0.0, drop_site: int = 0, rng=None):
-    """Fused attention backward (yv_attn_bwd); ``workspace`` is a zero-filled byte tensor of
-    ``attn_bwd_workspace_bytes`` bytes."""
+             tickets: torch.Tensor, passes: int = 3, drop_p: float = 0.0, drop_site: int = 0, rng=None):
+    """Fused attention backward (yv_attn_bwd); ``workspace`` is a byte tensor of ``attn_bwd_workspace_bytes`` bytes
+    (contents irrelevant), ``tickets`` an int32 tensor of pairs*heads zeros (left zero by the kernel)."""
     a = YvAttnBwd()
     a.pairs, a.heads, a.dh, a.passes = pairs, heads, dh, passes
     a.q, a.k, a.v, a.dout, a.out = q, k, v, dout, out
@@ -423,4 +424,6 @@ def attn_bwd(q: YvHeadView, k: YvHeadView, v: YvHeadView, dout: YvHeadView, out:
     a.lse = _p(lse)
     a.dq, a.dk, a.dv = dq, dk, dv
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    assert tickets.numel() >= pairs * heads and tickets.element_size() == 4
+    a.tickets = tickets.data_ptr()
     _check(load().yv_attn_bwd(C.byref(a), _stream()), "attn_bwd")

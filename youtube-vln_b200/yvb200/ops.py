@@ -52,8 +52,15 @@ class Runtime:
             raise RuntimeError(f"YVB200_PRECISION must be bf16x3 or bf16, got {mode}")
         self.passes = 3 if mode == "bf16x3" else 1
         self.attn_passes = int(os.environ.get("YVB200_ATTN_PASSES", self.passes))
-        seed = int(os.environ.get("YVB200_SEED", "20231117"))
-        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        # dropout RNG: {seed, step counter}.  ``master_rng`` is advanced once per training forward
+        # (``begin_training_forward``); ``rng`` is the snapshot the nodes of the current forward -- and later their
+        # backward, which regenerates the same masks -- read, so that a second forward issued before the first
+        # backward cannot change the masks of the first.  Ranks of a data-parallel job draw different masks: the
+        # default seed mixes in RANK (set YVB200_SEED to pin it).
+        seed = os.environ.get("YVB200_SEED")
+        seed = int(seed) if seed is not None else 20231117 + 7919 * int(os.environ.get("RANK", "0"))
+        self.master_rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self.rng = self.master_rng.clone()
         self.arena = WeightArena(device)
         # independent work (dgrad vs wgrad, text vs vision stream) is issued on helper CUDA streams so that the
         # captured step graph has parallel branches; YVB200_CONCURRENT=0 serialises everything on one stream
@@ -81,6 +88,7 @@ class Runtime:
         # reference and therefore takes the un-fused chain.  YVB200_FUSED_ATTN=0 forces the un-fused chain everywhere.
         self.fused_attention = os.environ.get("YVB200_FUSED_ATTN", "1") != "0"
         self.want_probs: Optional[bool] = None
+        self._tickets: Dict[int, torch.Tensor] = {}
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
         self.main_priority = -1 if prio else 0
         self.helper_priority = 0
@@ -135,12 +143,36 @@ class Runtime:
         self._helper_next[cur.cuda_stream] = (i + 1) % len(pool)
         return pool[i]
 
+    def attn_tickets(self, n: int) -> torch.Tensor:
+        """Zero-initialised ticket counters for one fused attention backward launch.  The kernel leaves them zero, so a
+        buffer is reusable by later launches on the SAME stream; launches on different streams may overlap and get
+        their own buffer (keyed by the issuing stream)."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        t = self._tickets.get(key)
+        if t is None or t.numel() < n:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("yvb200: attention ticket buffers must exist before graph capture (run a warm-up step)")
+            t = self._tickets[key] = torch.zeros(max(n, 4096), dtype=torch.int32, device=self.device)
+        return t
+
     def set_precision(self, mode: str):
         self.passes = 3 if mode == "bf16x3" else 1
         self.attn_passes = self.passes
 
     def advance_rng(self):
-        L.rng_advance(self.rng)
+        """Advance the step counter and give the next forward a fresh snapshot of {seed, counter}."""
+        L.rng_advance(self.master_rng)
+        self.rng = self.master_rng.clone()
+
+    begin_training_forward = advance_rng
+
+    def rng_state(self) -> torch.Tensor:
+        return self.master_rng.clone()
+
+    def set_rng_state(self, state: torch.Tensor):
+        """Restore a state returned by ``rng_state``: the next training forward draws the masks that followed it."""
+        self.master_rng.copy_(state)
+        self.rng = self.master_rng.clone()
 
 
 _RT: Dict[int, Runtime] = {}
@@ -198,6 +230,8 @@ class WeightArena:
         self.entries: Dict[Tuple[int, ...], _Entry] = {}
         self.always_stale = False      # bench: convert weights every step as real training would
         self.refresh_stream = None     # created on first overlapped refresh
+        self.skip_next_refresh = False  # set by a caller that has just refreshed everything itself (GraphedStep)
+        self.generation = 0            # bumped whenever an entry appears or disappears (FusedAdamW's pointer tables)
 
     def _alloc(self, n: int) -> Tuple[_Chunk, int]:
         n_al = (n + 63) // 64 * 64
@@ -215,6 +249,7 @@ class WeightArena:
         e.chunk.entries.remove(e)
         e.chunk.table = None
         del self.entries[key]
+        self.generation += 1
 
     def prune(self):
         """Forget the entries whose parameters no longer exist (their arena space is not reused)."""
@@ -254,6 +289,7 @@ class WeightArena:
             e.chunk.entries.append(e)
             e.chunk.table = None
             self.entries[key] = e
+            self.generation += 1
         c = e.chunk
         if c.ready is not None:        # this chunk is being re-split on the refresh stream: order this stream after it
             cur = torch.cuda.current_stream(self.device)
@@ -281,6 +317,15 @@ class WeightArena:
         for c in self.chunks:
             c.ready = None
             c.joined = set()
+
+    def refresh_for_forward(self, force: bool):
+        """Called at the start of every model forward.  ``force`` (training mode or autograd enabled) re-splits every
+        weight: optimizers that update through ``p.data`` (the reference's AdamW, vilbert/optimization.py:176-187) do
+        not bump ``p._version``, so version tracking alone would keep serving the initial planes."""
+        if self.skip_next_refresh:
+            self.skip_next_refresh = False
+            return
+        self.refresh_all(force=force)
 
     def refresh_all(self, force: bool = False, overlap: bool = False):
         """Re-split every chunk that holds a stale entry with one ``yv_split_multi`` launch.  With ``overlap`` the
@@ -393,34 +438,6 @@ class _EarlyOut:
         return self.zeroed
 
 
-class _ZeroedBytes:
-    """Zero-filled byte scratch; like ``_EarlyOut`` the fill runs on a forked stream as soon as the object is created and
-    ``ready()`` orders the issuing stream after it right before the consumer is launched."""
-    __slots__ = ("t", "_z", "_dev")
-
-    def __init__(self, r: "Runtime", nbytes: int, device):
-        self.t = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        self._dev = device
-        self._z = None
-        if r.concurrent and r.early_zero:
-            cur = torch.cuda.current_stream(device)
-            self._z = r.fork(2)
-            self._z.wait_stream(cur)
-            with torch.cuda.stream(self._z):
-                self.t.zero_()
-            self.t.record_stream(self._z)
-        else:
-            self.t.zero_()
-
-    def ready(self) -> torch.Tensor:
-        cur = torch.cuda.current_stream(self._dev)
-        if self._z is not None:
-            cur.wait_stream(self._z)
-            self._z = None
-        self.t.record_stream(cur)
-        return self.t
-
-
 def _keep_for(side: torch.cuda.Stream, *objs):
     """Tensors consumed (or produced) by work left running on ``side``: the caching allocator must not hand their
     memory to a later allocation of the issuing stream before that work has run."""
@@ -513,7 +530,7 @@ class DenseActFn(Function):
         M, N, K = ctx.dims
         dy2 = _c2d(dy)
         dp = Planes.empty(M, N, dy.device)
-        db = _f32(N, device=dy.device) if ctx.needs_input_grad[1] else None
+        db = _f32(N, device=dy.device) if ctx.needs_input_grad[2] else None
         L.act_bwd_split(dy2, ctx.aux, ctx.act, dp, db)
         dx, dW, db = _linear_bwd(r, dp, ctx.xp, ctx.wp, M, N, K, dy.device, ctx.needs_input_grad[0],
                                  ctx.needs_input_grad[1], db=db)
@@ -535,6 +552,7 @@ class DenseResLNFn(Function):
     @staticmethod
     def forward(ctx, x, res, W, b, gamma, beta, spec):
         r = rt(x.device)
+        ctx.rng = rng = r.rng
         x2 = _c2d(x)
         res2 = _c2d(res)
         M, K = x2.shape
@@ -543,7 +561,7 @@ class DenseResLNFn(Function):
         wp = r.arena.get((W,))
         s = _f32(M, N, device=x.device)
         L.gemm(M, N, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=b, residual=res2, out32=s, ld_out=N,
-               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng)
+               drop_p=spec.drop_p, drop_site=spec.site, rng=rng)
         z = _f32(M, N, device=x.device)
         zp = Planes.empty(M, N, x.device)
         stats = _f32(M, 2, device=x.device)
@@ -566,7 +584,7 @@ class DenseResLNFn(Function):
         dsp = Planes.empty(M, N, dev)
         acc = torch.zeros(3, N, dtype=torch.float32, device=dev)          # dgamma, dbeta, dbias in one memset
         L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, N, pre_drop_p=spec.drop_p,
-                        pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+                        pre_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
         dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2],
                                  db=acc[2], defer=True, dx_out=dx_out)
         return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, acc[0], acc[1], None
@@ -669,40 +687,32 @@ def _use_fused_attention(r: Runtime, dh: int) -> bool:
 
 
 def _attn_fwd(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Tensor, pairs: int, heads: int, dh: int,
-              drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]) -> _AttnSaved:
+              drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor], rng=None) -> _AttnSaved:
     """softmax(q k^T / sqrt(dh) + mask) v -> ``ctxp`` (merged heads): one fused launch, or GEMM -> softmax -> GEMM when
     the probabilities themselves are wanted (or the head size has no fused kernel)."""
     if _use_fused_attention(r, dh):
         lse = _f32(pairs * heads * q.S, device=mask.device)
         L.attn_fwd(q.view(), k.view(), v.view(), mask, pairs, heads, dh, 1.0 / math.sqrt(dh), ctxp, ctx32, lse,
-                   passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=r.rng)
+                   passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=rng)
         return _AttnSaved(True, lse=lse, mask=mask, ctxp=ctxp)
-    P, Pp = _attn_fwd_unfused(r, q, k, v, mask, pairs, heads, dh, drop_p, site, ctxp, ctx32)
+    P, Pp = _attn_fwd_unfused(r, q, k, v, mask, pairs, heads, dh, drop_p, site, ctxp, ctx32, rng)
     return _AttnSaved(False, P=P, Pp=Pp)
 
 
 def _attn_bwd(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, saved: _AttnSaved, pairs: int, heads: int,
-              dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView, fork_ok: bool = True,
-              workspace: Optional["_ZeroedBytes"] = None):
+              dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView, fork_ok: bool = True, rng=None):
     if saved.fused:
-        ws = workspace if workspace is not None else _ZeroedBytes(r, L.attn_bwd_workspace_bytes(pairs, heads, dh, k.S),
-                                                                  dOp.keep.device)
+        dev = dOp.keep.device
+        ws = torch.empty(L.attn_bwd_workspace_bytes(pairs, heads, dh, q.S, k.S), dtype=torch.uint8, device=dev)
         L.attn_bwd(q.view(), k.view(), v.view(), L.head_view(dOp, 0, q.S), L.head_view(saved.ctxp, 0, q.S), saved.mask,
-                   saved.lse, pairs, heads, dh, 1.0 / math.sqrt(dh), dq.view(), dk.view(), dv.view(), ws.ready(),
-                   passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=r.rng)
+                   saved.lse, pairs, heads, dh, 1.0 / math.sqrt(dh), dq.view(), dk.view(), dv.view(), ws,
+                   r.attn_tickets(pairs * heads), passes=r.attn_passes, drop_p=drop_p, drop_site=site, rng=rng)
         return
-    _attn_bwd_unfused(r, dOp, q, k, v, saved.P, saved.Pp, pairs, heads, dh, drop_p, site, dq, dk, dv, fork_ok)
-
-
-def _attn_workspace(r: Runtime, saved: _AttnSaved, pairs: int, heads: int, dh: int, Tk: int, device):
-    """Zero-filled scratch of the fused attention backward, filled early (off the dependency chain)."""
-    if not saved.fused:
-        return None
-    return _ZeroedBytes(r, L.attn_bwd_workspace_bytes(pairs, heads, dh, Tk), device)
+    _attn_bwd_unfused(r, dOp, q, k, v, saved.P, saved.Pp, pairs, heads, dh, drop_p, site, dq, dk, dv, fork_ok, rng)
 
 
 def _attn_fwd_unfused(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: torch.Tensor, pairs: int, heads: int, dh: int,
-                      drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor]):
+                      drop_p: float, site: int, ctxp: Planes, ctx32: Optional[torch.Tensor], rng=None):
     Tq, Tk = q.S, k.S
     ldS = (Tk + 7) // 8 * 8
     dev = mask.device
@@ -711,7 +721,7 @@ def _attn_fwd_unfused(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: t
            out32=S, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
     rows = pairs * heads * Tq
     Pp = Planes.empty(rows, Tk, dev, ld=ldS)
-    L.softmax_fwd(S, ldS, mask, rows, Tk, heads * Tq, 1.0 / math.sqrt(dh), Pp, drop_p, site, r.rng)
+    L.softmax_fwd(S, ldS, mask, rows, Tk, heads * Tq, 1.0 / math.sqrt(dh), Pp, drop_p, site, rng)
     Hout = heads * dh
     L.gemm(Tq, dh, Tk, _score_operand(Pp, Tq, Tk, ldS, pairs, heads, False), v.operand(pairs, heads, dh, True),
            passes=r.attn_passes, out32=ctx32, ld_out=Hout, out_sb0=dh, out_sb1=Tq * Hout, out_planes=ctxp.ptr(),
@@ -721,7 +731,7 @@ def _attn_fwd_unfused(r: Runtime, q: HeadView, k: HeadView, v: HeadView, mask: t
 
 def _attn_bwd_unfused(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: HeadView, P: torch.Tensor, Pp: Planes,
                       pairs: int, heads: int, dh: int, drop_p: float, site: int, dq: HeadView, dk: HeadView, dv: HeadView,
-                      fork_ok: bool = True):
+                      fork_ok: bool = True, rng=None):
     """dP -> softmax' -> dQ on the issuing stream; dV (needs only P and dO) and dK (needs dS) on a forked stream when
     ``fork_ok`` (callers that already run this function on a forked stream pass False)."""
     Tq, Tk = q.S, k.S
@@ -747,7 +757,7 @@ def _attn_bwd_unfused(r: Runtime, dOp: Planes, q: HeadView, k: HeadView, v: Head
     L.gemm(Tq, Tk, dh, dO.operand(pairs, heads, dh, False), v.operand(pairs, heads, dh, False), passes=r.attn_passes,
            out32=dPd, ld_out=ldS, out_sb0=Tq * ldS, out_sb1=heads * Tq * ldS)
     dSp = Planes.empty(rows, Tk, dev, ld=ldS)
-    L.softmax_bwd(P, dPd, ldS, rows, Tk, 1.0 / math.sqrt(dh), dSp, drop_p, site, r.rng)
+    L.softmax_bwd(P, dPd, ldS, rows, Tk, 1.0 / math.sqrt(dh), dSp, drop_p, site, rng)
     if side is not cur:
         side.wait_stream(cur)
     with torch.cuda.stream(side):
@@ -779,6 +789,7 @@ class SelfAttentionFn(Function):
     @staticmethod
     def forward(ctx, x, mask, Wq, bq, Wk, bk, Wv, bv, spec):
         r = rt(x.device)
+        ctx.rng = rng = r.rng
         pairs, S, K = x.shape
         H = Wq.shape[0]
         heads = spec.heads
@@ -794,7 +805,7 @@ class SelfAttentionFn(Function):
         c32 = _f32(M, H, device=x.device)
         cp = Planes.empty(M, H, x.device)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, c32)
+        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, c32, rng)
         ctx.r, ctx.xp, ctx.wp, ctx.qkv, ctx.att, ctx.spec = r, xp, wp, qkv, att, spec
         ctx.dims = (pairs, S, K, H, heads, dh)
         spec.out_planes = cp
@@ -807,13 +818,12 @@ class SelfAttentionFn(Function):
         pairs, S, K, H, heads, dh = ctx.dims
         M = pairs * S
         dev = dc.device
-        ws = _attn_workspace(r, ctx.att, pairs, heads, dh, S, dev)
         dOp = L.split_planes(_c2d(dc))
         dqkv = Planes.empty(M, 3 * H, dev)
         qkv = ctx.qkv
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
         _attn_bwd(r, dOp, q, k, v, ctx.att, pairs, heads, dh, spec.drop_p, spec.site,
-                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), workspace=ws)
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), rng=ctx.rng)
         dx, dW, db = _linear_bwd(r, dqkv, ctx.xp, ctx.wp, M, 3 * H, K, dev, ctx.needs_input_grad[0], True, defer=True)
         return ((dx.view(pairs, S, K) if dx is not None else None), None,
                 dW[:H], db[:H], dW[H:2 * H], db[H:2 * H], dW[2 * H:], db[2 * H:], None)
@@ -836,6 +846,7 @@ class AttnBlockFn(Function):
     @staticmethod
     def forward(ctx, x, mask, Wq, bq, Wk, bk, Wv, bv, Wo, bo, gamma, beta, spec):
         r = rt(x.device)
+        ctx.rng = rng = r.rng
         pairs, S, K = x.shape
         H = Wq.shape[0]
         heads = spec.heads
@@ -855,10 +866,10 @@ class AttnBlockFn(Function):
                out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
         cp = Planes.empty(M, H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
-        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None)
+        att = _attn_fwd(r, q, k, v, m2, pairs, heads, dh, spec.drop_p, spec.site, cp, None, rng)
         s = s_out.t
         L.gemm(M, H, H, L.op_of(cp), L.op_of(wo), passes=r.passes, bias=bo, residual=x2, out32=s, ld_out=H,
-               drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=r.rng, out32_zeroed=s_out.ready())
+               drop_p=spec.out_drop_p, drop_site=spec.out_site, rng=rng, out32_zeroed=s_out.ready())
         z = _f32(M, H, device=dev)
         zp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
@@ -880,12 +891,11 @@ class AttnBlockFn(Function):
         M = pairs * S
         dev = dz.device
         dx_out = _EarlyOut(r, M, K, 3 * H, dev) if ctx.needs_input_grad[0] else None
-        ws = _attn_workspace(r, att, pairs, heads, dh, S, dev)
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, d(out bias)
         L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.out_drop_p,
-                        pre_drop_site=spec.out_site, rng=r.rng, dbias=acc[2])
+                        pre_drop_site=spec.out_site, rng=ctx.rng, dbias=acc[2])
         dWo = _f32(H, H, device=dev)
         dOp = Planes.empty(M, H, dev)
         cur = torch.cuda.current_stream(dev)
@@ -899,7 +909,7 @@ class AttnBlockFn(Function):
         dqkv = Planes.empty(M, 3 * H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
         _attn_bwd(r, dOp, q, k, v, att, pairs, heads, dh, spec.drop_p, spec.site,
-                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), workspace=ws)
+                  HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), rng=ctx.rng)
         if side is not cur and r.defer_wgrad:
             _keep_for(side, dsp, cp, dWo)
             r.defer_join()
@@ -934,6 +944,7 @@ class FFNFn(Function):
     @staticmethod
     def forward(ctx, x, W1, b1, W2, b2, gamma, beta, spec):
         r = rt(x.device)
+        ctx.rng = rng = r.rng
         x2 = _c2d(x)
         M, H = x2.shape
         if x2.stride(0) != H:
@@ -950,7 +961,7 @@ class FFNFn(Function):
                out_planes=hp.ptr(), ld_pl=hp.ld, pl_plane_stride=hp.plane_stride)
         s = s_out.t
         L.gemm(M, H, FF, L.op_of(hp), L.op_of(w2), passes=r.passes, bias=b2, residual=x2, out32=s, ld_out=H,
-               drop_p=spec.drop_p, drop_site=spec.site, rng=r.rng, out32_zeroed=s_out.ready())
+               drop_p=spec.drop_p, drop_site=spec.site, rng=rng, out32_zeroed=s_out.ready())
         z = _f32(M, H, device=dev)
         zp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
@@ -974,7 +985,7 @@ class FFNFn(Function):
         dsp = Planes.empty(M, H, dev)
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, db2
         L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.drop_p,
-                        pre_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+                        pre_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
         dW2 = _f32(H, FF, device=dev)
         dW1 = _f32(FF, H, device=dev)
         db1 = _f32(FF, device=dev)
@@ -1019,6 +1030,7 @@ class BiAttentionFn(Function):
     @staticmethod
     def forward(ctx, xv, vmask, xt, tmask, Wq1, bq1, Wk1, bk1, Wv1, bv1, Wq2, bq2, Wk2, bk2, Wv2, bv2, spec):
         r = rt(xv.device)
+        ctx.rng = rng = r.rng
         pairs, V, Kv = xv.shape
         _, T, Kt = xt.shape
         H = Wq1.shape[0]
@@ -1051,8 +1063,8 @@ class BiAttentionFn(Function):
         cur.wait_stream(side)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            att1 = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1)
-        att2 = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2)
+            att1 = _attn_fwd(r, q2, k1, v1, vm, pairs, heads, dh, spec.drop_p1, spec.site1, c1p, c1, rng)
+        att2 = _attn_fwd(r, q1, k2, v2, tm, pairs, heads, dh, spec.drop_p2, spec.site2, c2p, c2, rng)
         cur.wait_stream(side)
         att1.keep_for(cur)
         ctx.r, ctx.spec = r, spec
@@ -1069,8 +1081,6 @@ class BiAttentionFn(Function):
         xvp, xtp, w1, w2, qkv1, qkv2, att1, att2 = ctx.keep
         dev = dc1.device
         Mv, Mt = pairs * V, pairs * T
-        ws1 = _attn_workspace(r, att1, pairs, heads, dh, V, dev)
-        ws2 = _attn_workspace(r, att2, pairs, heads, dh, T, dev)
         dxv_out = _EarlyOut(r, Mv, Kv, 3 * H, dev) if ctx.needs_input_grad[0] else None
         dxt_out = _EarlyOut(r, Mt, Kt, 3 * H, dev) if ctx.needs_input_grad[2] else None
         dO1 = L.split_planes(_c2d(dc1))
@@ -1085,8 +1095,8 @@ class BiAttentionFn(Function):
         side = r.fork() if r.concurrent else cur
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            _attn_bwd(r, dO1, q2, k1, v1, att1, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1, workspace=ws1)
-        _attn_bwd(r, dO2, q1, k2, v2, att2, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2, workspace=ws2)
+            _attn_bwd(r, dO1, q2, k1, v1, att1, pairs, heads, dh, spec.drop_p1, spec.site1, dq2, dk1, dv1, rng=ctx.rng)
+        _attn_bwd(r, dO2, q1, k2, v2, att2, pairs, heads, dh, spec.drop_p2, spec.site2, dq1, dk2, dv2, rng=ctx.rng)
         cur.wait_stream(side)
         dxv, dW1, db1 = _linear_bwd(r, d1, xvp, w1, Mv, 3 * H, Kv, dev, ctx.needs_input_grad[0], True, defer=True,
                                      dx_out=dxv_out)
@@ -1115,6 +1125,7 @@ class TextEmbedFn(Function):
     @staticmethod
     def forward(ctx, tok, seg, word, pos, typ, gamma, beta, spec):
         r = rt(word.device)
+        ctx.rng = rng = r.rng
         pairs, T = tok.shape
         H = word.shape[1]
         M = pairs * T
@@ -1125,7 +1136,7 @@ class TextEmbedFn(Function):
         y = _f32(M, H, device=dev)
         yp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
-        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, r.rng)
+        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, rng)
         ctx.r, ctx.spec, ctx.dims = r, spec, (pairs, T, H)
         ctx.shapes = (word.shape, pos.shape, typ.shape)
         ctx.save_for_backward(tok_c, seg_c, e, stats, gamma)
@@ -1143,7 +1154,7 @@ class TextEmbedFn(Function):
         dgamma = torch.zeros(H, dtype=torch.float32, device=dev)
         dbeta = torch.zeros(H, dtype=torch.float32, device=dev)
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, None, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
-                        post_drop_site=spec.site, rng=r.rng)
+                        post_drop_site=spec.site, rng=ctx.rng)
         dword = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev)
         dpos = torch.zeros(ctx.shapes[1], dtype=torch.float32, device=dev)
         dtyp = torch.zeros(ctx.shapes[2], dtype=torch.float32, device=dev)
@@ -1162,6 +1173,7 @@ class ImageEmbedFn(Function):
     @staticmethod
     def forward(ctx, feat, loc, Wi, bi, w5, b5, w4, b4, w2, b2, seq, gamma, beta, spec):
         r = rt(Wi.device)
+        ctx.rng = rng = r.rng
         pairs, V, F = feat.shape
         H = Wi.shape[0]
         M = pairs * V
@@ -1179,7 +1191,7 @@ class ImageEmbedFn(Function):
         y = _f32(M, H, device=dev)
         yp = Planes.empty(M, H, dev)
         stats = _f32(M, 2, device=dev)
-        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, r.rng)
+        L.layernorm_fwd(e, gamma, beta, LN_EPS, y, yp, stats, M, H, spec.drop_p, spec.site, rng)
         ctx.r, ctx.spec, ctx.dims, ctx.fp, ctx.wp = r, spec, (pairs, V, F, H), fp, wp
         ctx.save_for_backward(loc2, e, stats, gamma)
         spec.out_planes = yp
@@ -1197,7 +1209,7 @@ class ImageEmbedFn(Function):
         acc = torch.zeros(3, H, dtype=torch.float32, device=dev)
         dgamma, dbeta = acc[0], acc[1]
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, dep, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
-                        post_drop_site=spec.site, rng=r.rng, dbias=acc[2])
+                        post_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
         dfeat, dWi, dbi = _linear_bwd(r, dep, ctx.fp, ctx.wp, M, H, F, dev, ctx.needs_input_grad[0], True, db=acc[2])
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
         dw5, db5, dw4, db4, dw2, db2, dseq = z(H, 5), z(H), z(H, 4), z(H), z(H, 2), z(H), z(32, H)

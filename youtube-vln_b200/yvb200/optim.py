@@ -28,6 +28,19 @@ class FusedAdamW(Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias))
         self._tables = {}
 
+    def load_state_dict(self, state_dict):
+        self._tables.clear()
+        return super().load_state_dict(state_dict)
+
+    def add_param_group(self, param_group):
+        if hasattr(self, "_tables"):
+            self._tables.clear()
+        return super().add_param_group(param_group)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -82,10 +95,14 @@ class FusedAdamW(Optimizer):
         for p in ps:
             by_step.setdefault(self.state[p]["step"], []).append(p)
         for step, plist in by_step.items():
-            key = (gi, step == max(steps), tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist))
+            arena = ops.rt(dev).arena
+            # every raw pointer the kernel will dereference is part of the key: a replaced state tensor
+            # (load_state_dict), a re-allocated gradient or a new arena entry all rebuild the table
+            key = (gi, step == max(steps), arena.generation,
+                   tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                          self.state[p]["exp_avg_sq"].data_ptr()) for p in plist))
             tab = self._tables.get(key)
             if tab is None:
-                arena = ops.rt(dev).arena
                 planes = {}
                 arena.prune()
                 for e in arena.entries.values():          # GEMM weights: where their hi/lo planes live
@@ -104,7 +121,8 @@ class FusedAdamW(Optimizer):
                                             float(group["weight_decay"]), 0))
                     blk += (p.numel() + 2047) // 2048
                 raw = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).to(dev)
-                tab = (raw, len(rows), blk, torch.empty(7, dtype=torch.float32, device=dev), plist)
+                keep = [t for p in plist for t in (self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"])]
+                tab = (raw, len(rows), blk, torch.empty(7, dtype=torch.float32, device=dev), (plist, keep))
                 if len(self._tables) > 8:
                     self._tables.clear()
                 self._tables[key] = tab
@@ -113,5 +131,6 @@ class FusedAdamW(Optimizer):
             hyper.copy_(torch.tensor([group["lr"], self._step_size(group, step), b1, b2, group["eps"], 1.0 - b1, 1.0 - b2],
                                      dtype=torch.float32), non_blocking=True)
             lib.adamw_multi(raw, nseg, blocks, hyper)
-            # the kernel writes weights and planes through raw pointers: tensor versions do not move, so the arena
-            # keeps treating these planes as current (which they are)
+            # the kernel writes weights and planes through raw pointers (tensor versions do not move); a parameter
+            # without planes in this table (its arena entry did not exist yet) is re-split by the forced start-of-
+            # forward refresh of BertModel.forward, like with any other optimizer

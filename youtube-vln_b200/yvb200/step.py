@@ -206,10 +206,11 @@ class GraphedStep:
             p.grad = None
 
     def _body(self):
-        self.rt.advance_rng()
+        # (the dropout step counter is advanced by BertModel.forward itself, once per training forward)
         if self.refresh:
             # chunk 0 (first layers) on this stream, the rest overlapped with the start of the forward pass
             self.rt.arena.refresh_all(force=True, overlap=self.rt.concurrent)
+        self.rt.arena.skip_next_refresh = True      # the model's own start-of-forward refresh would repeat the work
         b = self.static
         if self.prefetch:
             # the next batch may be copied into the static buffers while this step is still running (see ``load``):
