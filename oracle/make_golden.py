@@ -263,9 +263,100 @@ def run_featstore():
     print("featstore golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")
 
 
+def run_variants():
+    """Less-travelled paths of the reference on the narrow ``micro`` model, complete tensors:
+      fixed/ : ``Lily`` with ``fixed_t_layer=1`` (frozen text prefix, vilbert/vilbert.py:745-764): outputs, losses, every
+               gradient, and which parameters get none;
+      attn/  : ``BertModel.forward(..., output_all_attention_masks=True)`` (vilbert/vilbert.py:1242-1337): every
+               attention-probability map of the three layer families plus the two pooled outputs;
+      vl/    : ``VILBertForVLTasks`` (vilbert/vilbert.py:1457-1520): the 7-tuple and the gradients of
+               sum_i mean(out_i^2) (the -10000 mask term of ``vision_logit`` is left out of the scalar)."""
+    vb, lily, ui = refload.load_reference()
+    wl = "micro"
+    cfgd = dict(synth.CONFIGS["micro"])
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=1)
+    out = {}
+
+    def mk_config(**over):
+        c = vb.BertConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in dict(cfgd, **over).items()})
+        c.args = args
+        return c
+
+    # ---- frozen text prefix
+    torch.manual_seed(0)
+    model = lily.Lily(mk_config(fixed_t_layer=1, fixed_v_layer=0))
+    synth.load_synthetic_weights(model, seed=0)
+    model.eval()
+    outputs = model(*ui.get_model_input(tuple(batch)))
+    total = 0.0
+    for task in ("vision", "language", "ranking", "traj"):
+        _, _, loss, _ = ui.get_loss_correct(tuple(batch), outputs, task, args, None, True)
+        out["fixed/loss/" + task] = np.float64(float(loss.detach()))
+        total = total + (args.traj_loss_scale * loss if task == "traj" else loss)
+    model.zero_grad()
+    total.backward()
+    out["fixed/total_loss"] = np.float64(float(total.detach()))
+    for k, v in outputs.items():
+        out["fixed/out/" + k] = v.detach().float().numpy()
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            out["fixed/nograd/" + name] = np.int8(1)
+        else:
+            out["fixed/grad/" + name] = p.grad.detach().float().numpy()
+
+    # ---- attention maps
+    torch.manual_seed(0)
+    model = lily.Lily(mk_config())
+    synth.load_synthetic_weights(model, seed=0)
+    model.eval()
+    inp = ui.get_model_input(tuple(batch))
+    with torch.no_grad():
+        seq_t, seq_v, pooled_t, pooled_v, (att_t, att_v, att_c) = model.bert(
+            inp[0], inp[1], inp[2], inp[3], inp[4], inp[5], inp[6], output_all_encoded_layers=False,
+            output_all_attention_masks=True)
+    out["attn/seq_t"], out["attn/seq_v"] = seq_t.numpy(), seq_v.numpy()
+    out["attn/pooled_t"], out["attn/pooled_v"] = pooled_t.numpy(), pooled_v.numpy()
+    for i, a in enumerate(att_t):
+        out[f"attn/t{i}"] = a.numpy()
+    for i, a in enumerate(att_v):
+        out[f"attn/v{i}"] = a.numpy()
+    for i, (a1, a2) in enumerate(att_c):
+        out[f"attn/c{i}_0"], out[f"attn/c{i}_1"] = a1.numpy(), a2.numpy()
+    out["attn/counts"] = np.array([len(att_t), len(att_v), len(att_c)])
+
+    # ---- VILBertForVLTasks
+    torch.manual_seed(0)
+    vl = vb.VILBertForVLTasks(mk_config(), num_labels=3, default_gpu=False)
+    synth.load_synthetic_weights(vl, seed=0)
+    vl.eval()
+    outs = vl(inp[0], inp[1], inp[2], inp[3], inp[4], inp[5], inp[6])
+    scalar = 0.0
+    for i, o in enumerate(outs):
+        out[f"vl/out{i}"] = o.detach().float().numpy()
+        if i == 4:      # vision_logit carries the additive -10000 mask: keep the unmasked entries only
+            m = (inp[5] > 0).unsqueeze(2).float()
+            scalar = scalar + ((o * m) ** 2).mean()
+        else:
+            scalar = scalar + (o ** 2).mean()
+    vl.zero_grad()
+    scalar.backward()
+    out["vl/scalar"] = np.float64(float(scalar.detach()))
+    for name, p in vl.named_parameters():
+        if p.grad is None:
+            out["vl/nograd/" + name] = np.int8(1)
+        else:
+            out["vl/grad/" + name] = p.grad.detach().float().numpy()
+    path = os.path.join(ROOT, "tests", "golden", "variants.npz")
+    np.savez_compressed(path, **out)
+    print("variants golden ->", path, f"({os.path.getsize(path)/1e3:.0f} KB)")
+
+
 if __name__ == "__main__":
-    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw", "masking", "featstore"]):
-        if wl == "adamw":
+    for wl in (sys.argv[1:] or ["micro", "cfg1", "cfg2", "adamw", "masking", "featstore", "variants"]):
+        if wl == "variants":
+            run_variants()
+        elif wl == "adamw":
             run_adamw()
         elif wl == "featstore":
             run_featstore()

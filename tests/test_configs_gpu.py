@@ -357,3 +357,69 @@ def test_degenerate_masks_match_oracle():
         if p.grad is None or float(o_grads[n].norm()) < 1e-6 * gmax:
             continue
         assert float((p.grad.cpu().double() - o_grads[n].double()).norm() / o_grads[n].double().norm()) < TOL, n
+
+
+def test_graphed_step_cfg2_matches_reference_golden(golden_dir):
+    """The path bench.py times -- yvb200.step.GraphedStep on the cfg2 workload, CUDA graph on (fused on-device losses,
+    overlapped plane refresh, trailing weight gradients, fused attention) -- against the golden vectors recorded from
+    the reference: total loss and every parameter gradient at 1e-3, on the first run and on a replay."""
+    _need_gpu()
+    import numpy as np
+    from test_oracle_golden import _check_grads
+    from yvb200.step import GraphedStep
+    g = np.load(__import__("os").path.join(golden_dir, "cfg2.npz"))
+    wl = "cfg2"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=1)
+    model = build_lily(cfg, args, device="cuda").eval()
+    step = GraphedStep(model, args, batch, use_graph=True, warmup=1)
+    for rep in range(2):
+        step.load(batch)
+        loss = step.run()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(g["total_loss"])) <= TOL * abs(float(g["total_loss"])), rep
+        grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters() if p.grad is not None}
+        assert _check_grads(g, grads, TOL) > 300
+
+
+def test_graphed_step_train_mode_matches_eager_with_same_rng():
+    """Train mode (dropout on), cfg2: the captured step draws the same counter-RNG masks as the eager
+    ``model(...)`` + ``backward()`` sequence started from the same RNG state, so loss and gradients agree to the
+    split-K reduction-order noise.  (The [N,1024] pooled dropout of the task wrapper uses torch's generator, whose
+    stream differs under capture: it is switched off for this comparison.)"""
+    _need_gpu()
+    from yvb200 import ops
+    from yvb200.step import GraphedStep
+    wl = "cfg2"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=3)
+    r = ops.rt("cuda")
+    model = build_lily(cfg, args, device="cuda").train()
+    model.dropout.p = 0.0
+    b = _dev(batch)
+    state = r.rng_state()
+    out = model(*synth.model_inputs(b))
+    ld = losses.step_losses(b, out, args, training=True)
+    tot = losses.total_loss(ld, args)
+    tot.backward()
+    want_loss = float(tot)
+    want = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    del out, ld, tot
+    # the SAME model object: dropout call sites are numbered per module instance, a second build would draw other masks
+    for p in model.parameters():
+        p.grad = None
+    step = GraphedStep(model, args, batch, use_graph=True, warmup=1)
+    r.set_rng_state(state)
+    loss = step.run()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - want_loss) < 2e-4 * abs(want_loss)
+    # and dropout is on: the eval-mode loss of the same batch is a different number
+    got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    assert set(got) == set(want)
+    gmax = max(float(v.norm()) for v in want.values())
+    for n, w in want.items():
+        if float(w.norm()) < 1e-6 * gmax:
+            continue
+        assert float((got[n] - w).norm()) < 2e-4 * float(w.norm()) + 1e-6 * gmax, n

@@ -39,8 +39,10 @@ def _run(wl, mode=None, train=False):
             model)
 
 
-@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1", "cfg2"])
+@pytest.mark.parametrize("wl", ["micro", "micro_pad", "cfg1", "cfg2", "cfg4_p16", "cfg4_p32"])
 def test_cuda_path_matches_reference_golden(golden_dir, wl):
+    """(cfg4_p16 / cfg4_p32: the trajectory-length sweep of BASELINE config 4 at its full batch of 8 pairs -- 576 and 1152
+    vision tokens per pair, the KV-chunked regime of the fused attention kernels.)"""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from yvb200 import lib
