@@ -423,3 +423,98 @@ def test_graphed_step_train_mode_matches_eager_with_same_rng():
         if float(w.norm()) < 1e-6 * gmax:
             continue
         assert float((got[n] - w).norm()) < 2e-4 * float(w.norm()) + 1e-6 * gmax, n
+
+
+def test_compacted_heads_match_full_logits():
+    """fused.language_head_loss / vision_head_loss evaluate the two big heads on the supervised rows only (NS3): same
+    loss and gradients as the full [N, T, 30522] / [N, V, 1601] logits path (d(logits) of an ignored row is exactly 0)."""
+    _need_gpu()
+    from yvb200.step import GraphedStep
+    wl = "cfg2"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=9)
+    res = {}
+    for fast in (False, True):
+        model = build_lily(cfg, args, device="cuda").eval()
+        step = GraphedStep(model, args, batch, use_graph=False, warmup=0, fast_heads=fast)
+        loss = step.run()
+        torch.cuda.synchronize()
+        res[fast] = (float(loss), {k: float(v) for k, v in step.losses.items()},
+                     {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+        del step, model
+    (l0, d0, g0), (l1, d1, g1) = res[False], res[True]
+    assert abs(l1 - l0) < 1e-5 * abs(l0)
+    for k in d0:
+        assert abs(d1[k] - d0[k]) < 1e-5 * max(1.0, abs(d0[k])), k
+    assert set(g0) == set(g1)
+    gmax = max(float(v.norm()) for v in g0.values())
+    for n in g0:
+        if float(g0[n].norm()) < 1e-6 * gmax:
+            continue
+        assert float((g1[n] - g0[n]).norm()) < 1e-4 * float(g0[n].norm()) + 1e-6 * gmax, n
+
+
+def test_compacted_heads_poison_the_loss_on_overflow():
+    """More supervised rows than the static capacity must not be dropped silently: the loss becomes NaN."""
+    _need_gpu()
+    from yvb200 import fused
+    import vilbert.vilbert as V
+    cfg = synth.TINY_CONFIG
+    config = V.BertConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items()})
+    head = V.BertLMPredictionHead(config, torch.nn.Embedding(cfg["vocab_size"], cfg["hidden_size"]).weight).cuda().eval()
+    seq = torch.randn(4, 80, cfg["hidden_size"], device="cuda")
+    tgt = torch.full((4, 80), -1, dtype=torch.long, device="cuda")
+    tgt[:, :20] = 7                                    # 80 supervised rows of 320, capacity 128
+    ok = fused.language_head_loss(head, seq, tgt)
+    full = fused.language_head_loss(head, seq, tgt, cap=320)
+    assert torch.isfinite(ok) and abs(float(ok) - float(full)) < 1e-5 * abs(float(full))
+    tgt[:, :40] = 7                                    # 160 supervised rows > 128
+    assert torch.isnan(fused.language_head_loss(head, seq, tgt))
+
+
+def test_graphed_step_with_padded_candidates_and_metrics():
+    """opt_mask with padded candidate slots (utils/utils_init.py:54-61): the captured step runs every slot and masks the
+    padded ones on the device; loss, gradients and the step metrics (utils/utils_init.py:136-189) match the eager
+    boolean-flattened path."""
+    _need_gpu()
+    from yvb200.step import GraphedStep
+    wl = "micro"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl, traj_judge=False)          # (the reference's traj BCE is NaN on -inf padded slots)
+    batch = synth.make_batch(wl, seed=4)
+    batch[13][1, 3] = False
+    batch[13][0, 2] = False
+    batch[0] = torch.tensor([1, 0])
+    model = build_lily(cfg, args, device="cuda").eval()
+    b = _dev(batch)
+    out = model(*synth.model_inputs(b))
+    ld = losses.step_losses(b, out, args, training=True)
+    tot = losses.total_loss(ld, args)
+    tot.backward()
+    want_loss = float(tot)
+    want = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    pred = losses.pad_packed(out["ranking"].squeeze(1).detach(), b[13])
+    want_correct = float((pred.argmax(1) == b[0]).sum())
+    want_ld = {k: float(v) for k, v in ld.items()}
+    del out, ld, tot
+    for p in model.parameters():
+        p.grad = None
+    step = GraphedStep(model, args, batch, use_graph=True, warmup=1)
+    for rep in range(2):
+        step.load(batch)
+        loss = step.run()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - want_loss) < 1e-4 * abs(want_loss), rep
+        got = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+        assert set(got) == set(want)
+        gmax = max(float(v.norm()) for v in want.values())
+        for n, w in want.items():
+            if float(w.norm()) < 1e-6 * gmax:
+                continue
+            assert float((got[n] - w).norm()) < 1e-4 * float(w.norm()) + 1e-6 * gmax, (rep, n)
+        m = step.metrics()
+        assert set(m["loss"]) == set(want_ld) and set(m["accuracy"]) == {"ranking"}
+        for k, v in want_ld.items():
+            assert abs(float(m["loss"][k]) - v) < 1e-4 * max(1.0, abs(v)), k
+        assert abs(float(m["accuracy"]["ranking"]) - want_correct / 2.0) < 1e-6

@@ -81,6 +81,70 @@ def vision_loss(logits: torch.Tensor, target: torch.Tensor, mask: torch.Tensor) 
     return KLLossFn.apply(_rows(logits), target.reshape(-1, target.shape[-1]), mask.reshape(-1))
 
 
+# ----------------------------------------------------------------------------------------------------
+# prediction heads + losses over the supervised rows only
+# ----------------------------------------------------------------------------------------------------
+def head_capacity(rows: int) -> int:
+    """Static row capacity of the compacted heads: 30 % of the rows, rounded up to whole 128-row GEMM tiles (masked-LM /
+    masked-region objectives supervise ~15 % of the positions; utils/dataset/common.py:213-300)."""
+    cap = (int(0.3 * rows) + 127) // 128 * 128
+    return max(128, min(cap, (rows + 127) // 128 * 128)) if rows > 128 else rows
+
+
+def compact_rows(sel: torch.Tensor, cap: int):
+    """Indices of the selected rows first (stable), truncated to ``cap`` -- a static shape, so the step stays
+    capturable.  Returns (idx [cap], overflow flag as a 0 / NaN scalar to add to the loss): rows beyond the selected
+    ones are fillers whose targets are "ignore", so they change nothing; if more than ``cap`` rows are selected the loss
+    is poisoned with NaN instead of silently dropping supervision."""
+    order = torch.argsort((~sel).to(torch.uint8), stable=True)
+    idx = order[:cap]
+    over = sel.sum() > cap
+    poison = torch.where(over, torch.full((), float("nan"), device=sel.device), torch.zeros((), device=sel.device))
+    return idx, poison
+
+
+def language_head_loss(head, seq_t: torch.Tensor, targets: torch.Tensor, cap: int = None) -> torch.Tensor:
+    """``cross_entropy(BertLMPredictionHead(seq_t), targets, ignore_index=-1)`` (vilbert/vilbert.py:889-907 +
+    utils/utils_init.py:129-135) evaluated on the supervised rows only: the transform, the 768 -> 30522 decoder, the
+    softmax passes and all three backward products shrink from N*T rows to ``cap`` rows (d(logits) of an ignored row is
+    exactly zero, so nothing is approximated).  ``head`` is the model's own ``cls.predictions`` module."""
+    rows = seq_t.reshape(-1, seq_t.shape[-1])
+    t = targets.reshape(-1)
+    cap = cap or head_capacity(rows.shape[0])
+    if cap >= rows.shape[0]:
+        return CELossFn.apply(_rows(head(rows)), t)
+    idx, poison = compact_rows(t != -1, cap)
+    logits = head(rows.index_select(0, idx))
+    return CELossFn.apply(_rows(logits), t.index_select(0, idx)) + poison
+
+
+def vision_head_loss(head, seq_v: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, cap: int = None) -> torch.Tensor:
+    """Masked-region KL loss (vilbert/vilbert.py:957-969 + utils/utils_init.py:117-128) on the masked regions only."""
+    rows = seq_v.reshape(-1, seq_v.shape[-1])
+    tg = target.reshape(-1, target.shape[-1])
+    m = mask.reshape(-1)
+    cap = cap or head_capacity(rows.shape[0])
+    if cap >= rows.shape[0]:
+        return KLLossFn.apply(_rows(head(rows)), tg, m)
+    idx, poison = compact_rows(m != 0, cap)
+    logits = head(rows.index_select(0, idx))
+    return KLLossFn.apply(_rows(logits), tg.index_select(0, idx), m.index_select(0, idx)) + poison
+
+
+def small_losses(batch: List[torch.Tensor], outputs: Dict[str, torch.Tensor], args, training: bool = True,
+                 correct: Dict[str, torch.Tensor] = None):
+    """Ranking / traj losses on ``[bs, C]`` logits computed for EVERY candidate slot (static shapes): padded
+    candidates are sent to -inf exactly like the reference's ``pad_packed`` (utils/dataset/common.py:21-26).
+    ``correct`` (optional dict) receives the accuracy counters of utils/utils_init.py:140-162 as device scalars."""
+    opt_mask = batch[13].bool()
+    bs, C = opt_mask.shape
+    outs = {}
+    for k in ("ranking", "traj"):
+        if k in outputs:
+            outs[k] = outputs[k].reshape(bs, C).masked_fill(~opt_mask, float("-inf"))
+    return _host_small_flat(batch, outs, args, training, bs, C, correct)
+
+
 def step_losses(batch: List[torch.Tensor], outputs: Dict[str, torch.Tensor], args, training: bool = True,
                 flat: bool = False):
     """Same dict as ``yvb200.losses.step_losses`` with the two big losses on the fused kernels.  ``flat=True``
@@ -104,13 +168,19 @@ def step_losses(batch: List[torch.Tensor], outputs: Dict[str, torch.Tensor], arg
     return res
 
 
-def _host_small_flat(batch, outputs, args, training, bs, C):
+def _host_small_flat(batch, outputs, args, training, bs, C, correct=None):
     import torch.nn.functional as F
     res = {}
     if "ranking" in outputs:
         pred = outputs["ranking"].reshape(bs, C)
-        res["ranking"] = (F.cross_entropy(pred, batch[0], ignore_index=-1) if training
-                          else F.binary_cross_entropy_with_logits(pred, batch[0].float()))
+        if training:
+            res["ranking"] = F.cross_entropy(pred, batch[0], ignore_index=-1)
+            if correct is not None:
+                correct["ranking"] = (pred.detach().argmax(1) == batch[0]).sum().float()
+        else:
+            res["ranking"] = F.binary_cross_entropy_with_logits(pred, batch[0].float())
+            if correct is not None:
+                correct["ranking"] = batch[0].gather(1, pred.detach().argmax(1).view(-1, 1)).sum().float()
     if "traj" in outputs:
         pred = outputs["traj"].reshape(bs, C)
         if not (args.ranking or args.not_traj_judge_data):
@@ -123,4 +193,6 @@ def _host_small_flat(batch, outputs, args, training, bs, C):
         target[:, :n_pos] = 1
         pos_weight = torch.full((1,), C / n_pos - 1, device=pred.device)
         res["traj"] = F.binary_cross_entropy_with_logits(pred, target, pos_weight=pos_weight)
+        if correct is not None:
+            correct["traj"] = ((pred.detach().sigmoid() > 0.5) == target.bool()).sum().float() / C
     return res

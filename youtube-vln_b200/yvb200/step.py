@@ -155,7 +155,7 @@ class GraphedStep:
 
     def __init__(self, model: torch.nn.Module, args, example_batch: List[torch.Tensor], use_graph: bool = True,
                  refresh_weights_each_step: bool = True, warmup: int = 2, exchange: Optional[GradientExchange] = None,
-                 prefetch: bool = True):
+                 prefetch: bool = True, fast_heads: Optional[bool] = None):
         self.model, self.args = model, args
         self.prefetch = prefetch
         self._consumed: List[torch.cuda.Event] = []
@@ -169,8 +169,15 @@ class GraphedStep:
         self.rt = ops.rt(self.device)
         self.refresh = refresh_weights_each_step
         self.static = [t.to(self.device).clone() if torch.is_tensor(t) else t for t in example_batch]
-        if not bool(self.static[13].all()):
-            raise RuntimeError("GraphedStep needs batches without padded candidates (opt_mask all ones)")
+        if fast_heads is None:
+            import os
+            fast_heads = os.environ.get("YVB200_FAST_HEADS", "1") != "0"
+        # the compacted-head path needs the Lily layout (bert / cls / vil_logit / judge); anything else runs generically
+        self.fast_heads = fast_heads and all(hasattr(model, a) for a in ("bert", "cls", "vil_logit", "judge", "dropout",
+                                                                          "fusion_method"))
+        if not self.fast_heads and not bool(self.static[13].all()):
+            raise RuntimeError("GraphedStep without fast_heads needs batches without padded candidates (opt_mask all ones)")
+        self.losses = {}
         self.loss = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
@@ -221,6 +228,41 @@ class GraphedStep:
         co = b[11]
         inputs = (b[6].flatten(0, 1), b[1].flatten(0, 1), b[2].flatten(0, 1), b[10].flatten(0, 1), b[7].flatten(0, 1),
                   b[3].flatten(0, 1), co.reshape(-1, co.size(2), co.size(3)), b[9].flatten(0, 1), b[15])
+        if self.fast_heads:
+            ld = self._forward_fast(b, inputs)
+        else:
+            ld = self._forward_generic(b, inputs)
+        tot = 0.0
+        for k in ("vision", "language", "ranking"):
+            if k in ld:
+                tot = tot + ld[k]
+        if "traj" in ld:
+            tot = tot + self.args.traj_loss_scale * ld["traj"]
+        self.losses = {k: v.detach() for k, v in ld.items()}
+        # metrics of the step (utils/utils_init.py:167-189) packed as [task, {loss, correct, batch size}] on the device:
+        # no .item(), and ONE all-reduce for all tasks when ``metrics`` is asked for (the reference issues three per task)
+        self.metric_tasks = [k for k in ("vision", "language", "ranking", "traj") if k in ld]
+        bsz = float(b[13].shape[0])
+        zero = torch.zeros((), device=self.device)
+        corr = getattr(self, "_correct", None) or {}
+        self.metric_pack = torch.stack([torch.stack([ld[k].detach().float(), corr.get(k, zero).float(),
+                                                     torch.full((), bsz, device=self.device)])
+                                        for k in self.metric_tasks])
+        if self.exchange is not None:
+            self.exchange.begin()
+        # weight gradients may trail on the helper streams: they are joined at segment ends by the exchange and at the
+        # end of the pass by the runtime's autograd callback
+        self.rt.defer_wgrad = self.rt.defer_wgrad_allowed
+        try:
+            tot.backward()
+        finally:
+            self.rt.defer_wgrad = False
+        if self.exchange is not None:
+            self.exchange.end()
+        self.loss = tot.detach()
+
+    def _forward_generic(self, b, inputs):
+        """Any model with the ``Lily`` call signature: full logits, fused loss kernels on all rows."""
         out = self.model(*inputs)
         self.rt.arena.join()
         if self.prefetch:
@@ -234,25 +276,61 @@ class GraphedStep:
                 ev = torch.cuda.Event(external=True)
                 ev.record(torch.cuda.current_stream(self.device))
                 self._consumed.append(ev)
-        ld = fused.step_losses(b, out, self.args, training=True, flat=True)
-        tot = 0.0
-        for k in ("vision", "language", "ranking"):
-            if k in ld:
-                tot = tot + ld[k]
-        if "traj" in ld:
-            tot = tot + self.args.traj_loss_scale * ld["traj"]
-        if self.exchange is not None:
-            self.exchange.begin()
-        # weight gradients may trail on the helper streams: they are joined at segment ends by the exchange and at the
-        # end of the pass by the runtime's autograd callback
-        self.rt.defer_wgrad = self.rt.defer_wgrad_allowed
-        try:
-            tot.backward()
-        finally:
-            self.rt.defer_wgrad = False
-        if self.exchange is not None:
-            self.exchange.end()
-        self.loss = tot.detach()
+        return fused.step_losses(b, out, self.args, training=True, flat=True)
+
+    def _forward_fast(self, b, inputs):
+        """``Lily.forward`` (lily.py:58-129) + ``get_loss_correct`` (utils/utils_init.py:108-164) composed from the
+        model's own sub-modules so that the two big heads only see their supervised rows (``fused.language_head_loss`` /
+        ``vision_head_loss``): the [N, T, 30522] and [N, V, 1601] logits of un-supervised positions -- 85 % of them --
+        are never computed.  Every candidate slot of the [bs, C] batch runs (static shapes); padded candidates
+        (``opt_mask``, utils/utils_init.py:54-61) are masked out of every loss on the device."""
+        m, args = self.model, self.args
+        seq_t, seq_v, pooled_t, pooled_v, _ = m.bert(
+            input_txt=inputs[0], input_imgs=inputs[1], image_loc=inputs[2], token_type_ids=inputs[3],
+            attention_mask=inputs[4], image_attention_mask=inputs[5], co_attention_mask=inputs[6],
+            output_all_encoded_layers=False)
+        self.rt.arena.join()
+        valid = b[13].flatten().bool()
+        ld = {}
+        cur = torch.cuda.current_stream(self.device)
+        side = self.rt.branch_stream if (self.rt.concurrent and args.masked_vision and args.masked_language) else None
+        if args.masked_vision:
+            tgt = b[4].flatten(0, 1)
+            rows = tgt.shape[0] * tgt.shape[1]
+            if self.prefetch and fused.head_capacity(rows) >= rows:
+                tgt = tgt.clone()                   # (no compaction: the loss backward would read the static buffer late)
+            msk = b[5].flatten(0, 1) * valid[:, None].to(b[5].dtype)
+            if side is not None:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ld["vision"] = fused.vision_head_loss(m.cls.imagePredictions, seq_v, tgt, msk)
+            else:
+                ld["vision"] = fused.vision_head_loss(m.cls.imagePredictions, seq_v, tgt, msk)
+        if args.masked_language:
+            lm_t = b[8].flatten(0, 1).masked_fill(~valid[:, None], -1)
+            ld["language"] = fused.language_head_loss(m.cls.predictions, seq_t, lm_t)
+        if side is not None:
+            cur.wait_stream(side)
+            ld["vision"].record_stream(cur)
+        if self.prefetch:                           # both big static inputs have been read for the last time
+            ev = torch.cuda.Event(external=True)
+            ev.record(cur)
+            self._consumed.append(ev)
+        if m.fusion_method == "sum":
+            pooled = pooled_t + pooled_v
+        elif m.fusion_method == "mul":
+            pooled = pooled_t * pooled_v
+        else:
+            assert False
+        pooled = m.dropout(pooled)
+        small = {}
+        if args.ranking:
+            small["ranking"] = m.vil_logit(pooled)
+        if args.traj_judge:
+            small["traj"] = m.judge(pooled)
+        self._correct = {}
+        ld.update(fused.small_losses(b, small, args, training=True, correct=self._correct))
+        return ld
 
     def load(self, batch: List[torch.Tensor]):
         """Copy a (pinned host or device) batch into the static buffers.  With ``prefetch`` the copy runs on its own
@@ -278,6 +356,22 @@ class GraphedStep:
                     dst.copy_(src, non_blocking=True)
             self._loaded = torch.cuda.Event()
             self._loaded.record(cs)
+
+    def metrics(self, reduce: bool = True):
+        """``reduced_metrics`` of the last step as the reference's ``compute_metrics_independent`` builds it
+        (utils/utils_init.py:167-189): ``{"loss": {task: mean over ranks}, "accuracy": {ranking / traj: correct / batch}}``
+        -- device scalars; with a gradient exchange attached the ranks are combined by a single packed all-reduce."""
+        pack = self.metric_pack.clone()
+        world = 1.0
+        if reduce and self.exchange is not None and self.exchange.world > 1:
+            world = float(self.exchange.world)
+            self.exchange.dist.all_reduce(pack, op=self.exchange.dist.ReduceOp.SUM, group=self.exchange.group)
+        out = {"loss": {}, "accuracy": {}}
+        for i, k in enumerate(self.metric_tasks):
+            out["loss"][k] = pack[i, 0] / world
+            if k not in ("vision", "language"):
+                out["accuracy"][k] = pack[i, 1] / pack[i, 2]
+        return out
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.static if torch.is_tensor(t))
