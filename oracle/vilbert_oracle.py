@@ -43,6 +43,15 @@ import torch.nn.functional as F
 
 LN_EPS = 1e-12
 
+#: dropout probability applied at the reference's 94 ``nn.Dropout`` sites; 0 = eval mode (every parity check).  Only
+#: bench.py's "stock PyTorch ops on the GPU" comparison switches it on (``oracle_step(..., train_dropout=True)``) so
+#: that the proxy pays for the same bernoulli kernels the reference's train-mode step issues.
+_DROP = {"p": 0.0}
+
+
+def _drop(x):
+    return F.dropout(x, _DROP["p"], True) if _DROP["p"] > 0.0 else x
+
 
 def gelu_erf(x):
     return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -75,7 +84,7 @@ def attention_core(q, k, v, add_mask, n_heads):
     qh, kh, vh = _heads(q, n_heads), _heads(k, n_heads), _heads(v, n_heads)
     dh = qh.shape[-1]
     scores = qh @ kh.transpose(-1, -2) / math.sqrt(dh) + add_mask
-    probs = torch.softmax(scores, dim=-1)
+    probs = _drop(torch.softmax(scores, dim=-1))
     return _merge(probs @ vh), probs
 
 
@@ -87,7 +96,7 @@ def self_attention(x, add_mask, sd, p, n_heads):
 
 
 def dense_res_ln(x, res, sd, p, ln="LayerNorm", dense="dense"):
-    return layer_norm(linear(x, sd, f"{p}.{dense}") + res, sd[f"{p}.{ln}.weight"], sd[f"{p}.{ln}.bias"])
+    return layer_norm(_drop(linear(x, sd, f"{p}.{dense}")) + res, sd[f"{p}.{ln}.weight"], sd[f"{p}.{ln}.bias"])
 
 
 def transformer_layer(x, add_mask, sd, p, n_heads):
@@ -104,8 +113,8 @@ def connection_layer(v, v_mask, t, t_mask, sd, p, n_heads):
     ctx1 = attention_core(q2, k1, v1, v_mask, n_heads)[0]          # text attends vision  [N,T,bi]
     ctx2 = attention_core(q1, k2, v2, t_mask, n_heads)[0]          # vision attends text  [N,V,bi]
     o = p + ".biOutput"
-    v_a = layer_norm(linear(ctx2, sd, o + ".dense1") + v, sd[o + ".LayerNorm1.weight"], sd[o + ".LayerNorm1.bias"])
-    t_a = layer_norm(linear(ctx1, sd, o + ".dense2") + t, sd[o + ".LayerNorm2.weight"], sd[o + ".LayerNorm2.bias"])
+    v_a = layer_norm(_drop(linear(ctx2, sd, o + ".dense1")) + v, sd[o + ".LayerNorm1.weight"], sd[o + ".LayerNorm1.bias"])
+    t_a = layer_norm(_drop(linear(ctx1, sd, o + ".dense2")) + t, sd[o + ".LayerNorm2.weight"], sd[o + ".LayerNorm2.bias"])
     v_o = dense_res_ln(gelu_erf(linear(v_a, sd, p + ".v_intermediate.dense")), v_a, sd, p + ".v_output")
     t_o = dense_res_ln(gelu_erf(linear(t_a, sd, p + ".t_intermediate.dense")), t_a, sd, p + ".t_output")
     return v_o, t_o
@@ -117,7 +126,7 @@ def text_embeddings(tokens, segs, sd, p="bert.embeddings"):
     e = F.embedding(tokens, sd[p + ".word_embeddings.weight"], padding_idx=0) \
         + sd[p + ".position_embeddings.weight"][pos][None] \
         + sd[p + ".token_type_embeddings.weight"][segs]
-    return layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"])
+    return _drop(layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"]))
 
 
 def image_embeddings(feat, loc, sd, p="bert.v_embeddings"):
@@ -126,7 +135,7 @@ def image_embeddings(feat, loc, sd, p="bert.v_embeddings"):
         + linear(loc[..., 5:9], sd, p + ".image_orientation_embeddings") \
         + linear(loc[..., 9:11], sd, p + ".image_next_orientation_embeddings") \
         + sd[p + ".image_sequence_embeddings.weight"][loc[..., 11].long()]
-    return layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"])
+    return _drop(layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"]))
 
 
 def bert_model(sd, cfg, tokens, feat, loc, segs=None, tmask=None, vmask=None):
@@ -171,7 +180,7 @@ def pretraining_heads(sd, seq_t, seq_v, pooled_t, pooled_v, fusion="mul"):
     g = gelu_erf(linear(seq_v, sd, q + ".transform.dense"))
     g = layer_norm(g, sd[q + ".transform.LayerNorm.weight"], sd[q + ".transform.LayerNorm.bias"])
     vis = linear(g, sd, q + ".decoder")
-    pooled = pooled_t * pooled_v if fusion == "mul" else pooled_t + pooled_v
+    pooled = _drop(pooled_t * pooled_v if fusion == "mul" else pooled_t + pooled_v)
     rel = linear(pooled, sd, "cls.bi_seq_relationship")
     return lm, vis, rel
 
@@ -180,7 +189,7 @@ def lily_forward(sd, cfg, args, tokens, feat, loc, segs=None, tmask=None, vmask=
     """Lily.forward (lily.py:58-129), eval mode (dropout = identity)."""
     seq_t, seq_v, pt, pv = bert_model(sd, cfg, tokens, feat, loc, segs, tmask, vmask)
     lm, vis, _ = pretraining_heads(sd, seq_t, seq_v, pt, pv, cfg.get("fusion_method", "mul"))
-    pooled = pt * pv if cfg.get("fusion_method", "mul") == "mul" else pt + pv
+    pooled = _drop(pt * pv if cfg.get("fusion_method", "mul") == "mul" else pt + pv)
     out = {}
     if args.ranking:
         out["ranking"] = linear(pooled, sd, "vil_logit")
@@ -256,10 +265,19 @@ def total_loss(loss_dict, args):
     return tot
 
 
-def oracle_step(sd: Dict[str, torch.Tensor], cfg, args, batch, dtype=torch.float32, want_grads=True, clone=True):
+def oracle_step(sd: Dict[str, torch.Tensor], cfg, args, batch, dtype=torch.float32, want_grads=True, clone=True,
+                train_dropout=False):
     """Forward + all active losses (+ autograd backward).  Returns (outputs, loss_dict, total, grads).
     Runs on whatever device ``sd`` / ``batch`` live on (the host for parity checks; bench.py also times it on
-    the GPU as the "stock PyTorch ops" comparison)."""
+    the GPU as the "stock PyTorch ops" comparison, there optionally with ``train_dropout``: p = 0.1 at all 94 sites)."""
+    _DROP["p"] = float(cfg.get("hidden_dropout_prob", 0.1)) if train_dropout else 0.0
+    try:
+        return _oracle_step(sd, cfg, args, batch, dtype, want_grads, clone)
+    finally:
+        _DROP["p"] = 0.0
+
+
+def _oracle_step(sd, cfg, args, batch, dtype, want_grads, clone):
     if clone:
         sd = {k: v.detach().to(dtype).clone().requires_grad_(want_grads) for k, v in sd.items()
               if not k.endswith("cls.predictions.decoder.weight")}

@@ -14,13 +14,17 @@ ops.rt("cuda").set_precision(mode)
 model = build_lily(cfg, args, device="cuda").train()
 batch = synth.make_batch(wl, seed=1)
 st = GraphedStep(model, args, batch, use_graph=False, warmup=2)
-lib.GEMM_TRACE = []
-torch.cuda._sleep(int(6e8))
-st.run()
-torch.cuda.synchronize()
-tr, lib.GEMM_TRACE = lib.GEMM_TRACE, None
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import devtools
+with devtools.trace_gemms() as tr:
+    torch.cuda._sleep(int(6e8))
+    st.run()
+    torch.cuda.synchronize()
 agg = collections.OrderedDict()
-for M, N, K, B, P, e0, e1 in tr:
+for name, shape, fl, e0, e1 in tr:
+    if name != "yv_gemm":
+        continue
+    M, N, K, B, P = shape
     k = (M, N, K, B, P)
     c, t = agg.get(k, (0, 0.0))
     agg[k] = (c + 1, t + e0.elapsed_time(e1))

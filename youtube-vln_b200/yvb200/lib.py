@@ -74,8 +74,6 @@ class YvSplitSeg(C.Structure):
 
 
 _lib = None
-#: when set to a list, ``gemm`` appends (M, N, K, batch, passes, start_event, end_event) per launch
-GEMM_TRACE = None
 
 
 def load():
@@ -96,36 +94,8 @@ def load():
     for name in SYMBOLS:
         if not hasattr(lib, name):
             raise RuntimeError(f"yvb200: {LIB_PATH} does not export {name}")
-    _lib = _LibProxy(lib)
+    _lib = lib
     return _lib
-
-
-#: bench.py's roofline leg: when True every entry point except yv_gemm returns without launching, so that a captured
-#: step contains the GEMM launches only (their operands are then uninitialised memory: timing only, never results)
-ONLY_GEMM = False
-_ALWAYS = {"yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_rng_advance",
-           "yv_attn_supported", "yv_attn_bwd_workspace_bytes"}
-
-
-class _LibProxy:
-    """Attribute access to the CDLL with the ONLY_GEMM switch applied to the non-GEMM launchers."""
-
-    def __init__(self, cdll):
-        self._cdll = cdll
-        for name in SYMBOLS:
-            fn = getattr(cdll, name)
-            if name in _ALWAYS:
-                setattr(self, name, fn)
-            else:
-                setattr(self, name, self._skippable(fn))
-
-    @staticmethod
-    def _skippable(fn):
-        def call(*args):
-            if ONLY_GEMM:
-                return 0
-            return fn(*args)
-        return call
 
 
 def available() -> bool:
@@ -206,17 +176,7 @@ def gemm(M: int, N: int, K: int, a: YvOperand, b: YvOperand, *, passes: int = 3,
     g.ld_pl, g.pl_sb0, g.pl_sb1, g.pl_plane_stride = ld_pl, pl_sb0, pl_sb1, pl_plane_stride
     g.drop_p, g.drop_site, g.rng = drop_p, drop_site, _p(rng)
     g.out32_zeroed = 1 if out32_zeroed else 0
-    if GEMM_TRACE is None:
-        _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
-    elif ONLY_GEMM:   # bench.py's roofline leg: shapes only (the launches are being captured into a GEMM-only graph)
-        _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
-        GEMM_TRACE.append((M, N, K, int(a.nb0 * a.nb1), passes, None, None))
-    else:   # developer tracing: bracket every GEMM launch with CUDA events on the launching stream
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
-        e1.record()
-        GEMM_TRACE.append((M, N, K, int(a.nb0 * a.nb1), passes, e0, e1))
+    _check(load().yv_gemm(C.byref(g), _stream()), "gemm")
 
 
 _SPLIT_CACHE = {}

@@ -75,6 +75,21 @@ WORKLOADS = {
 }
 
 
+def derive_workload(base: str, pairs: int) -> str:
+    """Register (once) and name the variant of ``base`` with ``pairs`` trajectory-instruction pairs per batch: BASELINE
+    configs 3 / 5 fix the GLOBAL batch (16 / 64 pairs), so the per-GPU batch depends on the number of ranks."""
+    if pairs == WORKLOADS[base]["bs"] * WORKLOADS[base]["cands"]:
+        return base
+    name = f"{base}@{pairs}"
+    if name not in WORKLOADS:
+        cands = 4 if pairs % 4 == 0 else (2 if pairs % 2 == 0 else 1)
+        w = dict(WORKLOADS[base], bs=pairs // cands, cands=cands)
+        if cands < 3:                       # two candidates: fine-tune style traj target (as in cfg1)
+            w["args"] = dict(w.get("args", {}), pretrain=False)
+        WORKLOADS[name] = w
+    return name
+
+
 def workload_args(workload: str, **over) -> types.SimpleNamespace:
     """``make_args`` with the per-workload overrides (cfg1 has 2 candidates -> fine-tune style traj target)."""
     kw = dict(WORKLOADS[workload].get("args", {}))
