@@ -37,6 +37,13 @@ def test_library_exports_every_declared_symbol():
     assert h.yv_gemm(None, None) != 0 and b"NULL" in h.yv_last_error()
     assert h.yv_gemm_set_variant(C.c_int(7)) != 0 and b"variant" in h.yv_last_error()
     assert h.yv_gemm_set_variant(C.c_int(0)) == 0
+    # fused attention: supported head sizes, workspace query and argument checks (no device work)
+    assert h.yv_attn_supported(C.c_int32(128), C.c_int32(3)) == 1 and h.yv_attn_supported(C.c_int32(96), C.c_int32(3)) == 0
+    assert lib.attn_bwd_workspace_bytes(8, 8, 128, 288, 288) == 3 * 8 * 288 * 2 * 1024 * 4
+    assert h.yv_attn_fwd(None, None) != 0 and b"NULL" in h.yv_last_error()
+    bad = lib.YvAttnFwd()
+    bad.pairs, bad.heads, bad.dh, bad.passes = 1, 1, 96, 3
+    assert h.yv_attn_fwd(C.byref(bad), None) != 0 and b"head size" in h.yv_last_error()
 
 
 def test_ctypes_structs_match_the_header_layout(tmp_path):
@@ -49,6 +56,11 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
                    "ld_out", "out_sb0", "out_sb1", "out_planes", "ld_pl", "pl_sb0", "pl_sb1", "pl_plane_stride", "drop_p",
                    "drop_site", "rng", "out32_zeroed"],
         "YvSplitSeg": ["src", "dst_off", "numel", "first_blk"],
+        "YvHeadView": ["ptr", "ld", "plane_stride", "pair_stride", "rows"],
+        "YvAttnFwd": ["pairs", "heads", "dh", "passes", "q", "k", "v", "mask", "scale", "drop_p", "drop_site", "rng",
+                      "out_planes", "ld_out", "out_plane_stride", "out32", "ld_out32", "lse"],
+        "YvAttnBwd": ["pairs", "heads", "dh", "passes", "q", "k", "v", "dout", "out", "mask", "scale", "drop_p", "drop_site",
+                      "rng", "lse", "dq", "dk", "dv", "workspace", "workspace_bytes", "tickets"],
         "YvAdamSeg": ["p", "g", "m", "v", "plane_hi", "plane_lo", "numel", "first_blk", "weight_decay"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
@@ -62,7 +74,8 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(probe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
-    mirrors = {"YvOperand": lib.YvOperand, "YvGemm": lib.YvGemm, "YvSplitSeg": lib.YvSplitSeg}
+    mirrors = {"YvOperand": lib.YvOperand, "YvGemm": lib.YvGemm, "YvSplitSeg": lib.YvSplitSeg,
+               "YvHeadView": lib.YvHeadView, "YvAttnFwd": lib.YvAttnFwd, "YvAttnBwd": lib.YvAttnBwd}
     for line in out:
         name, size, *offs = line.split()
         if name == "YvAdamSeg":        # yvb200/optim.py packs these rows with struct.pack("<QQQQQQqqfi", ...)

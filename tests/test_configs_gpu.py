@@ -518,3 +518,48 @@ def test_graphed_step_with_padded_candidates_and_metrics():
         for k, v in want_ld.items():
             assert abs(float(m["loss"][k]) - v) < 1e-4 * max(1.0, abs(v)), k
         assert abs(float(m["accuracy"]["ranking"]) - want_correct / 2.0) < 1e-6
+
+
+def test_two_devices_in_one_process():
+    """The reference falls back to nn.DataParallel (utils/distributed.py:100-102): forward is then called from one host
+    thread per device inside ONE process, so every launcher must be re-entrant per device (per-device shared-memory
+    opt-in, SM count, runtime state).  Needs two visible GPUs."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    import threading
+    wl = "cfg1"
+    cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+    args = synth.workload_args(wl)
+    batch = synth.make_batch(wl, seed=2)
+    models = [build_lily(cfg, args, device=f"cuda:{i}").eval() for i in range(2)]
+    results = [None, None]
+    errors = []
+
+    def work(i):
+        try:
+            with torch.cuda.device(i):
+                b = [t.to(f"cuda:{i}") if torch.is_tensor(t) else t for t in batch]
+                out = models[i](*synth.model_inputs(b))
+                ld = losses.step_losses(b, out, args, training=True)
+                tot = losses.total_loss(ld, args)
+                tot.backward()
+                torch.cuda.synchronize(i)
+                results[i] = (float(tot), {n: p.grad.detach().cpu() for n, p in models[i].named_parameters()
+                                           if p.grad is not None})
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    (l0, g0), (l1, g1) = results
+    assert abs(l0 - l1) < 1e-4 * abs(l0)
+    gmax = max(float(v.norm()) for v in g0.values())
+    for n in g0:
+        if float(g0[n].norm()) < 1e-6 * gmax:
+            continue
+        assert float((g0[n] - g1[n]).norm()) < 1e-4 * float(g0[n].norm()) + 1e-6 * gmax, n

@@ -6,6 +6,7 @@ copied into static device buffers (the host->device boundary of utils/utils_init
 counter is advanced inside the graph, and every weight is re-split to bf16 planes inside the graph (weights change
 every optimiser step).  Gradients land in the parameters' ``.grad`` (static storage owned by the graph pool).
 """
+import os
 from typing import List, Optional
 
 import torch
@@ -30,7 +31,7 @@ class GradientExchange:
         import os
         import torch.distributed as dist
         if segment_mb is None:
-            segment_mb = float(os.environ.get("YVB200_SEGMENT_MB", "160"))
+            segment_mb = float(os.environ.get("YVB200_SEGMENT_MB", "320"))
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group)
         self.segment_bytes = int(segment_mb * 2 ** 20)
@@ -39,23 +40,36 @@ class GradientExchange:
         self.cuda = self.device.type == "cuda"
         self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.nccl = dist.get_backend(group) == "nccl"
+        # YVB200_EXCHANGE_DTYPE=bf16 (opt-in): half the bytes over NVLink, at bf16 rounding (2^-9 relative) of every
+        # averaged gradient element -- NOT the reference's fp32 DistributedDataParallel arithmetic
+        self.payload = os.environ.get("YVB200_EXCHANGE_DTYPE", "fp32")
+        if self.payload not in ("fp32", "bf16"):
+            raise RuntimeError("YVB200_EXCHANGE_DTYPE must be fp32 or bf16")
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in model.parameters()
                         if p.requires_grad]
         self.recording = False
         self.segments = []          # [(event or None, [grads])] of the step being issued / captured
         self.pending: List[torch.Tensor] = []
+        self.pending_params: List[torch.Tensor] = []
+        self.segment_params: List[List[torch.Tensor]] = []
         self.pending_bytes = 0
         self.launched = 0
+        self._flat = None           # (bucket, [views per segment], [slice per segment]) of the flat exchange buffer
+        # YVB200_EXCHANGE_FLAT=0: one all-reduce per gradient tensor, grouped per segment (round-1 behaviour)
+        self.flat = os.environ.get("YVB200_EXCHANGE_FLAT", "1") != "0"
 
     # ---- called while the step is being issued (eagerly or under capture)
     def begin(self):
         self.recording = True
         self.segments, self.pending, self.pending_bytes = [], [], 0
+        self.pending_params, self.segment_params = [], []
+        self._flat = None
 
     def _on_grad(self, p: torch.Tensor):
         if not self.recording or p.grad is None:
             return
         self.pending.append(p.grad)
+        self.pending_params.append(p)
         self.pending_bytes += p.grad.numel() * p.grad.element_size()
         if self.overlap and self.pending_bytes >= self.segment_bytes:
             self._close_segment(with_event=True)
@@ -82,15 +96,57 @@ class GradientExchange:
                 ev.record(s_)
                 evs.append(ev)
         self.segments.append((evs, self.pending))
-        self.pending, self.pending_bytes = [], 0
+        self.segment_params.append(self.pending_params)
+        self.pending, self.pending_bytes, self.pending_params = [], 0, []
 
     def end(self):
         """Close the last segment (it is covered by the completion of the step itself)."""
         self._close_segment(with_event=False)
         self.recording = False
 
+    def _build_flat(self):
+        """One contiguous exchange buffer in backward order: each segment is a slice, each gradient a view of it.  NCCL
+        then sees ONE large all-reduce per segment (full-bandwidth protocol; with many per-tensor operations grouped into
+        one launch it falls back to the low-latency protocols that move half the payload per byte on the wire)."""
+        dt = torch.bfloat16 if self.payload == "bf16" else torch.float32
+        total = sum(g.numel() for _, grads in self.segments for g in grads)
+        bucket = torch.empty(total, dtype=dt, device=self.device)
+        views, slices, off = [], [], 0
+        for _, grads in self.segments:
+            start, vs = off, []
+            for g in grads:
+                vs.append(bucket[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            views.append(vs)
+            slices.append(bucket[start:off])
+        self._flat = (bucket, views, slices)
+
     # ---- called after the step has been launched (after graph.replay() or the eager body)
     def exchange(self):
+        if self.cuda and self.nccl and self.flat:
+            if self._flat is None:
+                self._build_flat()
+            _, views, slices = self._flat
+            main = torch.cuda.current_stream(self.device)
+            for i, (evs, grads) in enumerate(self.segments):
+                if evs is not None:
+                    for ev in evs:
+                        self.comm.wait_event(ev)
+                else:
+                    self.comm.wait_stream(main)
+                with torch.cuda.stream(self.comm):
+                    torch._foreach_copy_(views[i], grads)               # gather (and cast) into the flat slice
+                    self.dist.all_reduce(slices[i], op=self.dist.ReduceOp.AVG, group=self.group)
+                    if self.payload == "bf16":
+                        torch._foreach_copy_(grads, views[i])           # back to the fp32 gradients
+                self.launched += 1
+            main.wait_stream(self.comm)
+            if self.payload != "bf16":
+                # the averaged gradients live in the flat buffer: hand those views to the parameters (no copy back)
+                for ps, vs in zip(self.segment_params, views):
+                    for p, v in zip(ps, vs):
+                        p.grad = v
+            return
         if self.cuda:
             main = torch.cuda.current_stream(self.device)
             for evs, grads in self.segments:
@@ -110,6 +166,17 @@ class GradientExchange:
 
     def _reduce(self, grads):
         dist = self.dist
+        if self.nccl and self.payload == "bf16":
+            total = sum(g.numel() for g in grads)
+            bucket = torch.empty(total, dtype=torch.bfloat16, device=self.device)
+            views, off = [], 0
+            for g in grads:
+                views.append(bucket[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(views, grads)
+            dist.all_reduce(bucket, op=dist.ReduceOp.AVG, group=self.group)
+            torch._foreach_copy_(grads, views)
+            return
         if self.nccl:                               # one grouped launch, averaging inside the collective
             with dist._coalescing_manager(group=self.group, device=self.device, async_ops=False):
                 for g in grads:
