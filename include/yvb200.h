@@ -146,6 +146,16 @@ int yv_layernorm_bwd(const float* dy, const float* x, const float* gamma, const 
                      const uint64_t* rng, float* dgamma, float* dbeta, float* dbias, int64_t M, int32_t C,
                      yv_stream_t stream);
 
+/* The same backward in two launches (autograd of vilbert/vilbert.py:204-217 again): _dx computes only what the rest of the
+ * backward pass waits for (dx, dx_planes); _cols accumulates dgamma / dbeta (zero-initialised by the caller) and can trail
+ * on another stream next to the weight gradients.  (The bias gradient of the preceding dense layer is then
+ * yv_colsum_planes of dx_planes.) */
+int yv_layernorm_bwd_dx(const float* dy, const float* x, const float* gamma, const float* stats, const float* dx_add,
+                        float* dx32, void* dx_planes, int64_t plane_stride, float pre_drop_p, uint32_t pre_drop_site,
+                        const uint64_t* rng, int64_t M, int32_t C, yv_stream_t stream);
+int yv_layernorm_bwd_cols(const float* dy, const float* x, const float* stats, float* dgamma, float* dbeta, int64_t M,
+                          int32_t C, yv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * attention softmax (vilbert/vilbert.py:295-304, 424-433, 578-589, 598-611):
  *   P = softmax(S * scale + mask[pair, key]); S is overwritten by P (kept for backward);

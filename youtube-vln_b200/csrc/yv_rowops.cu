@@ -408,7 +408,7 @@ layernorm_fwd_warp_kernel(const float* __restrict__ x, const float* __restrict__
 // Backward: each warp walks rows (grid-stride over warps); the column sums dgamma / dbeta / dbias stay in registers per
 // lane, are combined across the block's warps through shared memory and leave as one vector reduction per block and
 // column group.
-template <int NV>
+template <int NV, bool COLS>
 __global__ void __launch_bounds__(LNW_WARPS * 32)
 layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                           const float* __restrict__ stats, float post_p, unsigned post_site,
@@ -448,8 +448,10 @@ layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict_
                     d.z *= yv_drop_mul(dpost, i0 + 2); d.w *= yv_drop_mul(dpost, i0 + 3);
                 }
                 xh[j] = make_float4((xv.x - mean) * rs, (xv.y - mean) * rs, (xv.z - mean) * rs, (xv.w - mean) * rs);
-                ag[j].x += d.x * xh[j].x; ag[j].y += d.y * xh[j].y; ag[j].z += d.z * xh[j].z; ag[j].w += d.w * xh[j].w;
-                ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
+                if (COLS) {
+                    ag[j].x += d.x * xh[j].x; ag[j].y += d.y * xh[j].y; ag[j].z += d.z * xh[j].z; ag[j].w += d.w * xh[j].w;
+                    ab[j].x += d.x; ab[j].y += d.y; ab[j].z += d.z; ab[j].w += d.w;
+                }
                 g[j] = make_float4(d.x * gm[j].x, d.y * gm[j].y, d.z * gm[j].z, d.w * gm[j].w);
                 s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
                 s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
@@ -473,7 +475,7 @@ layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] *= yv_drop_mul(dpre, i0 + e);
             }
-            abias[j].x += o[0]; abias[j].y += o[1]; abias[j].z += o[2]; abias[j].w += o[3];
+            if (COLS) { abias[j].x += o[0]; abias[j].y += o[1]; abias[j].z += o[2]; abias[j].w += o[3]; }
             if (dxp) {
                 __align__(8) __nv_bfloat16 h4[4], l4[4];
 #pragma unroll
@@ -483,6 +485,7 @@ layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict_
             }
         }
     }
+    if (!COLS) return;
     // block-level column sums: one array and one column group at a time through 4 KB of shared memory
 #pragma unroll
     for (int which = 0; which < 3; ++which) {
@@ -508,6 +511,47 @@ layernorm_bwd_warp_kernel(const float* __restrict__ dy, const float* __restrict_
             }
             __syncthreads();
         }
+    }
+}
+
+// dgamma[c] += sum_m dy[m, c] * xhat[m, c],  dbeta[c] += sum_m dy[m, c]  -- the column reductions of the LayerNorm
+// backward as a kernel of their own: nothing on the dependency chain of the backward pass needs them, so the step issues
+// them on a trailing stream next to the weight gradients while layernorm_bwd_warp_kernel<NV, false> (dx only, a third of
+// the registers, four blocks per SM) stays on the chain.  blockIdx.x = 128-column group, blockIdx.y = row split.
+__global__ void __launch_bounds__(LNW_WARPS * 32)
+layernorm_bwd_cols_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                          float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C, int rows_per_split) {
+    yv_pdl_trigger();
+    yv_pdl_wait();
+    __shared__ float4 red[2][LNW_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_split;
+    const long long r1 = min(M, r0 + rows_per_split);
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    if (c < C) {
+        for (long long row = r0 + warp; row < r1; row += LNW_WARPS) {
+            const float mean = __ldg(stats + 2 * row), rs = __ldg(stats + 2 * row + 1);
+            const float4 d = *reinterpret_cast<const float4*>(dy + row * C + c);
+            const float4 xv = *reinterpret_cast<const float4*>(x + row * C + c);
+            ag.x += d.x * ((xv.x - mean) * rs); ag.y += d.y * ((xv.y - mean) * rs);
+            ag.z += d.z * ((xv.z - mean) * rs); ag.w += d.w * ((xv.w - mean) * rs);
+            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+        }
+    }
+    red[0][warp][lane] = ag;
+    red[1][warp][lane] = ab;
+    __syncthreads();
+    if (warp < 2 && c < C) {
+        float4 t = red[warp][0][lane];
+#pragma unroll
+        for (int w = 1; w < LNW_WARPS; ++w) {
+            const float4 u = red[warp][w][lane];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        float* out = warp == 0 ? dgamma : dbeta;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                     : "memory");
     }
 }
 
@@ -1199,7 +1243,7 @@ extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* ga
         __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dx_planes);
         const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
         const int nv = (C + 127) / 128;
-#define YV_LNB(NV) YV_CUDA(yv_launch(layernorm_bwd_warp_kernel<NV>, grid, block, 0, S(stream), dy, x, gamma, stats, post_drop_p, \
+#define YV_LNB(NV) YV_CUDA(yv_launch(layernorm_bwd_warp_kernel<NV, true>, grid, block, 0, S(stream), dy, x, gamma, stats, post_drop_p, \
                                      post_drop_site, dx_add, dx32, dp, plane_stride, pre_drop_p, pre_drop_site, r, dgamma, dbeta, \
                                      dbias, M, C))
         if (nv <= 2) YV_LNB(2); else if (nv <= 4) YV_LNB(4); else if (nv <= 6) YV_LNB(6); else YV_LNB(8);
@@ -1212,6 +1256,41 @@ extern "C" int yv_layernorm_bwd(const float* dy, const float* x, const float* ga
                                                           reinterpret_cast<__nv_bfloat16*>(dx_planes), plane_stride, pre_drop_p,
                                                           pre_drop_site, reinterpret_cast<const unsigned long long*>(rng), dgamma,
                                                           dbeta, dbias, M, C));
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_layernorm_bwd_dx(const float* dy, const float* x, const float* gamma, const float* stats,
+                                   const float* dx_add, float* dx32, void* dx_planes, int64_t plane_stride, float pre_drop_p,
+                                   uint32_t pre_drop_site, const uint64_t* rng, int64_t M, int32_t C, yv_stream_t stream) {
+    YV_CHECK(dy && x && gamma && stats && M > 0 && C > 0, "yv_layernorm_bwd_dx: bad arguments");
+    YV_CHECK(C <= 1024 && C % 4 == 0, "yv_layernorm_bwd_dx: hidden size %d must be a multiple of 4 and <= 1024", C);
+    YV_CHECK(((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)gamma | (uintptr_t)dx_add | (uintptr_t)dx32) & 15) == 0) &&
+                 ((((uintptr_t)dx_planes) & 7) == 0) && (plane_stride % 4 == 0),
+             "yv_layernorm_bwd_dx: pointers must be 16-byte aligned");
+    const dim3 grid((unsigned)grid_for(M, LNW_WARPS, 148 * 4)), block(LNW_WARPS * 32);
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dx_planes);
+    const unsigned long long* r = reinterpret_cast<const unsigned long long*>(rng);
+    const int nv = (C + 127) / 128;
+#define YV_LNB(NV) YV_CUDA(yv_launch(layernorm_bwd_warp_kernel<NV, false>, grid, block, 0, S(stream), dy, x, gamma, stats, 0.f, \
+                                     0u, dx_add, dx32, dp, plane_stride, pre_drop_p, pre_drop_site, r, (float*)nullptr, \
+                                     (float*)nullptr, (float*)nullptr, M, C))
+    if (nv <= 2) YV_LNB(2); else if (nv <= 4) YV_LNB(4); else if (nv <= 6) YV_LNB(6); else YV_LNB(8);
+#undef YV_LNB
+    YV_LAUNCHED();
+}
+
+extern "C" int yv_layernorm_bwd_cols(const float* dy, const float* x, const float* stats, float* dgamma, float* dbeta,
+                                     int64_t M, int32_t C, yv_stream_t stream) {
+    YV_CHECK(dy && x && stats && dgamma && dbeta && M > 0 && C > 0, "yv_layernorm_bwd_cols: bad arguments");
+    YV_CHECK(C % 4 == 0 && ((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0),
+             "yv_layernorm_bwd_cols: hidden size must be a multiple of 4 and pointers 16-byte aligned");
+    const int groups = (C + 127) / 128;
+    int splits = (2 * 148 + groups - 1) / groups;
+    if ((long long)splits * LNW_WARPS > M) splits = (int)((M + LNW_WARPS - 1) / LNW_WARPS);
+    const int rows_per_split = (int)((M + splits - 1) / splits);
+    splits = (int)((M + rows_per_split - 1) / rows_per_split);
+    YV_CUDA(yv_launch(layernorm_bwd_cols_kernel, dim3((unsigned)groups, (unsigned)splits), dim3(LNW_WARPS * 32), 0, S(stream),
+                      dy, x, stats, dgamma, dbeta, M, C, rows_per_split));
     YV_LAUNCHED();
 }
 

@@ -872,6 +872,8 @@ class BertModel(BertPreTrainedModel):
             if self.training:
                 # fresh dropout masks for this forward (its backward regenerates them from the same snapshot)
                 r.begin_training_forward()
+            if torch.is_grad_enabled():
+                r.begin_zero_slab()         # zero-initialised reduction buffers of the backward pass, one memset
         # additive masks: 0 where attended, -10000 where padded (reference :1268-1287)
         ext_t = (1.0 - attention_mask.unsqueeze(1).unsqueeze(2).to(dtype=torch.float32)) * -10000.0
         ext_v = (1.0 - image_attention_mask.unsqueeze(1).unsqueeze(2).to(dtype=torch.float32)) * -10000.0

@@ -20,7 +20,7 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_MUL_GELU_GRAD, ACT_MUL_RELU_MASK = 0, 1, 2, 3,
 #: every symbol include/yvb200.h declares (tests check the built library exports all of them)
 SYMBOLS = [
     "yv_last_error", "yv_version", "yv_launch_count", "yv_gemm", "yv_gemm_splits", "yv_gemm_set_variant", "yv_split_planes", "yv_split_multi",
-    "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_softmax_fwd", "yv_softmax_bwd",
+    "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_layernorm_bwd_dx", "yv_layernorm_bwd_cols", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
     "yv_mask_tokens", "yv_mask_regions", "yv_attn_supported", "yv_attn_fwd", "yv_attn_bwd", "yv_attn_bwd_workspace_bytes",
@@ -245,6 +245,22 @@ def layernorm_bwd(dy, x, gamma, stats, dx32, dx_planes: Optional[Planes], dgamma
                                    C.c_float(pre_drop_p), C.c_uint32(pre_drop_site), C.c_void_p(_p(rng)),
                                    C.c_void_p(_p(dgamma)), C.c_void_p(_p(dbeta)), C.c_void_p(_p(dbias)), C.c_int64(M),
                                    C.c_int32(Cdim), _stream()), "layernorm_bwd")
+
+
+def layernorm_bwd_dx(dy, x, gamma, stats, dx32, dx_planes: Optional[Planes], M, Cdim, *, dx_add=None, pre_drop_p=0.0,
+                     pre_drop_site=0, rng=None):
+    _check(load().yv_layernorm_bwd_dx(C.c_void_p(dy.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()),
+                                      C.c_void_p(stats.data_ptr()), C.c_void_p(_p(dx_add)), C.c_void_p(_p(dx32)),
+                                      C.c_void_p(dx_planes.ptr() if dx_planes is not None else None),
+                                      C.c_int64(dx_planes.plane_stride if dx_planes is not None else 0),
+                                      C.c_float(pre_drop_p), C.c_uint32(pre_drop_site), C.c_void_p(_p(rng)), C.c_int64(M),
+                                      C.c_int32(Cdim), _stream()), "layernorm_bwd_dx")
+
+
+def layernorm_bwd_cols(dy, x, stats, dgamma, dbeta, M, Cdim):
+    _check(load().yv_layernorm_bwd_cols(C.c_void_p(dy.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(stats.data_ptr()),
+                                        C.c_void_p(dgamma.data_ptr()), C.c_void_p(dbeta.data_ptr()), C.c_int64(M),
+                                        C.c_int32(Cdim), _stream()), "layernorm_bwd_cols")
 
 
 def softmax_fwd(s, ld_s, mask, rows, cols, rows_per_pair, scale, p_planes: Planes, drop_p=0.0, drop_site=0, rng=None):

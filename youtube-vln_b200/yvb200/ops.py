@@ -87,6 +87,7 @@ class Runtime:
         # output_all_attention_masks); None = a sub-module called on its own, which returns probabilities like the
         # reference and therefore takes the un-fused chain.  YVB200_FUSED_ATTN=0 forces the un-fused chain everywhere.
         self.fused_attention = os.environ.get("YVB200_FUSED_ATTN", "1") != "0"
+        self.ln_split = os.environ.get("YVB200_LN_SPLIT", "1") != "0"
         self.want_probs: Optional[bool] = None
         self._tickets: Dict[int, torch.Tensor] = {}
         prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
@@ -142,6 +143,25 @@ class Runtime:
         i = self._helper_next[cur.cuda_stream]
         self._helper_next[cur.cuda_stream] = (i + 1) % len(pool)
         return pool[i]
+
+    # ---- zero-initialised accumulators of the backward pass (dgamma / dbeta / dbias reductions) ------------------
+    ZERO_SLAB = 1 << 20            # floats: one 4 MB memset per training forward instead of ~70 memset nodes on the chain
+
+    def begin_zero_slab(self):
+        """Called at the start of a forward pass that will be differentiated: the backward nodes carve their
+        zero-initialised reduction buffers out of this slab (``zeros``) instead of issuing a memset each."""
+        self._zslab = torch.zeros(self.ZERO_SLAB, dtype=torch.float32, device=self.device)
+        self._zoff = 0
+
+    def zeros(self, rows: int, cols: int) -> torch.Tensor:
+        n = rows * cols
+        n_al = (n + 63) // 64 * 64
+        slab = getattr(self, "_zslab", None)
+        if slab is None or self._zoff + n_al > slab.numel():
+            return torch.zeros(rows, cols, dtype=torch.float32, device=self.device)
+        t = slab[self._zoff:self._zoff + n].view(rows, cols)
+        self._zoff += n_al
+        return t
 
     def attn_tickets(self, n: int) -> torch.Tensor:
         """Zero-initialised ticket counters for one fused attention backward launch.  The kernel leaves them zero, so a
@@ -231,6 +251,7 @@ class WeightArena:
         self.always_stale = False      # bench: convert weights every step as real training would
         self.refresh_stream = None     # created on first overlapped refresh
         self.skip_next_refresh = False  # set by a caller that has just refreshed everything itself (GraphedStep)
+        self.bias_cats: Dict[Tuple[int, ...], Tuple[torch.Tensor, tuple, list]] = {}   # fused Q|K|V biases
         self.generation = 0            # bumped whenever an entry appears or disappears (FusedAdamW's pointer tables)
 
     def _alloc(self, n: int) -> Tuple[_Chunk, int]:
@@ -318,6 +339,43 @@ class WeightArena:
             c.ready = None
             c.joined = set()
 
+    def bias_cat(self, biases: Tuple[torch.Tensor, ...]) -> torch.Tensor:
+        """fp32 concatenation of the biases of a fused projection (Q|K|V), kept next to the weight planes and refreshed
+        with them by ``refresh_all`` -- instead of one ``torch.cat`` launch in front of every projection GEMM."""
+        key = tuple(id(b) for b in biases)
+        ent = self.bias_cats.get(key)
+        if ent is not None:
+            live = tuple(r() for r in ent[1])
+            if any(a is not b for a, b in zip(live, biases)):
+                ent = None
+        if ent is None:
+            buf = torch.cat([b.detach() for b in biases])
+            views, off = [], 0
+            for b in biases:
+                views.append(buf[off:off + b.numel()])
+                off += b.numel()
+            ent = self.bias_cats[key] = (buf, tuple(weakref.ref(b) for b in biases), views)
+            self._bias_versions = None
+        return ent[0]
+
+    def _refresh_biases(self, force: bool):
+        if not self.bias_cats:
+            return
+        dst, src, vers = [], [], []
+        for key, (buf, refs, views) in list(self.bias_cats.items()):
+            live = tuple(r() for r in refs)
+            if any(b is None for b in live):
+                del self.bias_cats[key]
+                continue
+            dst.extend(views)
+            src.extend(b.detach() for b in live)
+            vers.extend((b._version, b.data_ptr()) for b in live)
+        if not force and getattr(self, "_bias_versions", None) == vers:
+            return
+        if dst:
+            torch._foreach_copy_(dst, src)
+        self._bias_versions = vers
+
     def refresh_for_forward(self, force: bool):
         """Called at the start of every model forward.  ``force`` (training mode or autograd enabled) re-splits every
         weight: optimizers that update through ``p.data`` (the reference's AdamW, vilbert/optimization.py:176-187) do
@@ -333,6 +391,7 @@ class WeightArena:
         a separate stream while the forward pass starts; ``get`` orders each consumer stream after its chunk."""
         force = force or self.always_stale
         self.prune()
+        self._refresh_biases(force)
         cur = torch.cuda.current_stream(self.device)
         if overlap and len(self.chunks) > 1:
             if self.refresh_stream is None:
@@ -448,9 +507,27 @@ def _keep_for(side: torch.cuda.Stream, *objs):
         t.record_stream(side)
 
 
+def _ln_bwd_chain(r: Runtime, dz2, s, gamma, stats, ds, dsp, acc, M, C, drop_p, site, rng):
+    """LayerNorm backward of a dense -> dropout -> (+residual) -> LN block, split in two: the part the backward chain
+    waits for (ds and its dropped planes) is launched now; the returned closure issues the column reductions
+    (dgamma, dbeta -> acc[0], acc[1]; bias gradient of the dense layer -> acc[2]) and is meant to run on the trailing
+    stream of the caller, next to the weight gradient.  YVB200_LN_SPLIT=0 keeps the single fused kernel."""
+    if not r.ln_split:
+        L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, C, pre_drop_p=drop_p, pre_drop_site=site, rng=rng,
+                        dbias=acc[2])
+        return lambda: None
+    L.layernorm_bwd_dx(dz2, s, gamma, stats, ds, dsp, M, C, pre_drop_p=drop_p, pre_drop_site=site, rng=rng)
+
+    def cols():
+        L.layernorm_bwd_cols(dz2, s, stats, acc[0], acc[1], M, C)
+        L.colsum_planes(dsp, acc[2], accumulate=True)
+    return cols
+
+
 def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int, N: int, K: int, device,
                 need_dx: bool, need_dw: bool, dx_residual: Optional[torch.Tensor] = None,
-                db: Optional[torch.Tensor] = None, defer: bool = False, dx_out: Optional["_EarlyOut"] = None):
+                db: Optional[torch.Tensor] = None, defer: bool = False, dx_out: Optional["_EarlyOut"] = None,
+                side_first=None, side_keep=()):
     """dx = dp . W ;  dW = dp^T . x ;  db = colsum(dp)   with dp [M,N], W [N,K], x [M,K].
     ``db`` may arrive precomputed (fused into the kernel that produced ``dp``).  With ``defer`` the weight / bias
     gradient is left running on the helper stream (joined at the end of the backward pass, see Runtime.defer_join)."""
@@ -473,17 +550,21 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
         side = r.helper() if trailing else r.fork()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
+            if side_first is not None:
+                side_first()
             L.gemm(N, K, M, L.op_of(dp, True), L.op_of(xp, True), passes=r.passes, out32=dW, ld_out=K)
             if not have_db:
                 L.colsum_planes(dp, db)
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual,
                out32_zeroed=dx_zeroed)
         if trailing:
-            _keep_for(side, dp, xp, dW, None if have_db else db)
+            _keep_for(side, dp, xp, dW, None if have_db else db, *side_keep)
             r.defer_join()
         else:
             cur.wait_stream(side)
         return dx, dW, db
+    if side_first is not None:
+        side_first()
     if need_dx:
         L.gemm(M, K, N, L.op_of(dp), L.op_of(wp, True), passes=r.passes, out32=dx, ld_out=K, residual=dx_residual,
                out32_zeroed=dx_zeroed)
@@ -582,11 +663,10 @@ class DenseResLNFn(Function):
         dx_out = _EarlyOut(r, M, K, N, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, N, device=dev)
         dsp = Planes.empty(M, N, dev)
-        acc = torch.zeros(3, N, dtype=torch.float32, device=dev)          # dgamma, dbeta, dbias in one memset
-        L.layernorm_bwd(dz2, s, gamma, stats, ds, dsp, acc[0], acc[1], M, N, pre_drop_p=spec.drop_p,
-                        pre_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
+        acc = r.zeros(3, N)                                               # dgamma, dbeta, dbias
+        cols = _ln_bwd_chain(r, dz2, s, gamma, stats, ds, dsp, acc, M, N, spec.drop_p, spec.site, ctx.rng)
         dx, dW, db = _linear_bwd(r, dsp, ctx.xp, ctx.wp, M, N, K, dev, ctx.needs_input_grad[0], ctx.needs_input_grad[2],
-                                 db=acc[2], defer=True, dx_out=dx_out)
+                                 db=acc[2], defer=True, dx_out=dx_out, side_first=cols, side_keep=(dz2, s, stats, acc))
         return (dx.view(ctx.xshape) if dx is not None else None), ds.view(ctx.rshape), dW, db, acc[0], acc[1], None
 
 
@@ -629,8 +709,8 @@ class DenseActLNFn(Function):
         pre, g, stats, gamma = ctx.saved_tensors
         dev = dz.device
         dg = _f32(M, N, device=dev)
-        dgamma = torch.zeros(N, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(N, dtype=torch.float32, device=dev)
+        acc = r.zeros(2, N)
+        dgamma, dbeta = acc[0], acc[1]
         L.layernorm_bwd(_c2d(dz), g, gamma, stats, dg, None, dgamma, dbeta, M, N)
         dp = Planes.empty(M, N, dev)
         aux = pre if ctx.act == L.ACT_GELU else g
@@ -781,8 +861,8 @@ def _mask2d(mask: torch.Tensor, pairs: int, Tk: int) -> torch.Tensor:
     return m.contiguous()
 
 
-def _cat_bias(bs):
-    return torch.cat([b.detach() for b in bs])
+def _cat_bias(r: "Runtime", bs):
+    return r.arena.bias_cat(tuple(bs))
 
 
 class SelfAttentionFn(Function):
@@ -800,7 +880,7 @@ class SelfAttentionFn(Function):
         wp = r.arena.get((Wq, Wk, Wv))
         m2 = _mask2d(mask, pairs, S)
         qkv = Planes.empty(M, 3 * H, x.device)
-        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=_cat_bias((bq, bk, bv)),
+        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wp), passes=r.passes, bias=_cat_bias(r, (bq, bk, bv)),
                out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
         c32 = _f32(M, H, device=x.device)
         cp = Planes.empty(M, H, x.device)
@@ -862,7 +942,7 @@ class AttnBlockFn(Function):
         m2 = _mask2d(mask, pairs, S)
         s_out = _EarlyOut(r, M, H, H, dev)
         qkv = Planes.empty(M, 3 * H, dev)
-        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wqkv), passes=r.passes, bias=_cat_bias((bq, bk, bv)),
+        L.gemm(M, 3 * H, K, L.op_of(xp), L.op_of(wqkv), passes=r.passes, bias=_cat_bias(r, (bq, bk, bv)),
                out_planes=qkv.ptr(), ld_pl=qkv.ld, pl_plane_stride=qkv.plane_stride)
         cp = Planes.empty(M, H, dev)
         q, k, v = HeadView(qkv, 0, S), HeadView(qkv, H, S), HeadView(qkv, 2 * H, S)
@@ -893,15 +973,16 @@ class AttnBlockFn(Function):
         dx_out = _EarlyOut(r, M, K, 3 * H, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
-        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, d(out bias)
-        L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.out_drop_p,
-                        pre_drop_site=spec.out_site, rng=ctx.rng, dbias=acc[2])
+        acc = r.zeros(3, H)                                               # dgamma, dbeta, d(out bias)
+        dz2 = _c2d(dz)
+        cols = _ln_bwd_chain(r, dz2, s, gamma, stats, ds, dsp, acc, M, H, spec.out_drop_p, spec.out_site, ctx.rng)
         dWo = _f32(H, H, device=dev)
         dOp = Planes.empty(M, H, dev)
         cur = torch.cuda.current_stream(dev)
         side = (r.helper() if r.defer_wgrad else r.fork()) if r.concurrent else cur
         side.wait_stream(cur)
-        with torch.cuda.stream(side):                                     # wgrad of the output projection
+        with torch.cuda.stream(side):                                     # LN column sums, wgrad of the output projection
+            cols()
             L.gemm(H, H, M, L.op_of(dsp, True), L.op_of(cp, True), passes=r.passes, out32=dWo, ld_out=H)
         # dgrad of the output projection straight into the planes the attention backward reads
         L.gemm(M, H, H, L.op_of(dsp), L.op_of(wo, True), passes=r.passes, out_planes=dOp.ptr(), ld_pl=dOp.ld,
@@ -911,7 +992,7 @@ class AttnBlockFn(Function):
         _attn_bwd(r, dOp, q, k, v, att, pairs, heads, dh, spec.drop_p, spec.site,
                   HeadView(dqkv, 0, S), HeadView(dqkv, H, S), HeadView(dqkv, 2 * H, S), rng=ctx.rng)
         if side is not cur and r.defer_wgrad:
-            _keep_for(side, dsp, cp, dWo)
+            _keep_for(side, dsp, cp, dWo, dz2, s, stats, acc)
             r.defer_join()
         else:
             cur.wait_stream(side)
@@ -983,9 +1064,9 @@ class FFNFn(Function):
         dx_out = _EarlyOut(r, M, H, FF, dev) if ctx.needs_input_grad[0] else None
         ds = _f32(M, H, device=dev)
         dsp = Planes.empty(M, H, dev)
-        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)          # dgamma, dbeta, db2
-        L.layernorm_bwd(_c2d(dz), s, gamma, stats, ds, dsp, acc[0], acc[1], M, H, pre_drop_p=spec.drop_p,
-                        pre_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
+        acc = r.zeros(3, H)                                               # dgamma, dbeta, db2
+        dz2 = _c2d(dz)
+        cols = _ln_bwd_chain(r, dz2, s, gamma, stats, ds, dsp, acc, M, H, spec.drop_p, spec.site, ctx.rng)
         dW2 = _f32(H, FF, device=dev)
         dW1 = _f32(FF, H, device=dev)
         db1 = _f32(FF, device=dev)
@@ -993,7 +1074,8 @@ class FFNFn(Function):
         cur = torch.cuda.current_stream(dev)
         side = (r.helper() if r.defer_wgrad else r.fork()) if r.concurrent else cur
         side.wait_stream(cur)
-        with torch.cuda.stream(side):                                     # dW2 = ds^T . h
+        with torch.cuda.stream(side):                                     # LN column sums, dW2 = ds^T . h
+            cols()
             L.gemm(H, FF, M, L.op_of(dsp, True), L.op_of(hp, True), passes=r.passes, out32=dW2, ld_out=FF)
         # d(pre) = (ds . W2) * gelu'(pre), written as planes only
         L.gemm(M, FF, H, L.op_of(dsp), L.op_of(w2, True), passes=r.passes, act=L.ACT_MUL_GELU_GRAD, aux_in=pre, ld_out=FF,
@@ -1008,7 +1090,7 @@ class FFNFn(Function):
             L.gemm(M, H, FF, L.op_of(dprep), L.op_of(w1, True), passes=r.passes, out32=dx, ld_out=H, residual=ds,
                    out32_zeroed=dx_out.ready())
         if side is not cur and r.defer_wgrad:
-            _keep_for(side, dsp, hp, dW2, dprep, xp, dW1, db1)
+            _keep_for(side, dsp, hp, dW2, dprep, xp, dW1, db1, dz2, s, stats, acc)
             r.defer_join()
         else:
             cur.wait_stream(side)
@@ -1044,7 +1126,7 @@ class BiAttentionFn(Function):
         w2 = r.arena.get((Wq2, Wk2, Wv2))
         qkv1 = Planes.empty(Mv, 3 * H, dev)
         qkv2 = Planes.empty(Mt, 3 * H, dev)
-        b1c, b2c = _cat_bias((bq1, bk1, bv1)), _cat_bias((bq2, bk2, bv2))
+        b1c, b2c = _cat_bias(r, (bq1, bk1, bv1)), _cat_bias(r, (bq2, bk2, bv2))
         vm, tm = _mask2d(vmask, pairs, V), _mask2d(tmask, pairs, T)
         c1 = _f32(Mt, H, device=dev)
         c1p = Planes.empty(Mt, H, dev)
@@ -1151,8 +1233,8 @@ class TextEmbedFn(Function):
         M = pairs * T
         dev = dy.device
         de = _f32(M, H, device=dev)
-        dgamma = torch.zeros(H, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(H, dtype=torch.float32, device=dev)
+        acc = r.zeros(2, H)
+        dgamma, dbeta = acc[0], acc[1]
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, None, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
                         post_drop_site=spec.site, rng=ctx.rng)
         dword = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev)
@@ -1206,7 +1288,7 @@ class ImageEmbedFn(Function):
         dev = dy.device
         de = _f32(M, H, device=dev)
         dep = Planes.empty(M, H, dev)
-        acc = torch.zeros(3, H, dtype=torch.float32, device=dev)
+        acc = r.zeros(3, H)
         dgamma, dbeta = acc[0], acc[1]
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, dep, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
                         post_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
