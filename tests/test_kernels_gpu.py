@@ -230,6 +230,16 @@ def test_layernorm_fwd_bwd(L, M, Cd):
     assert _rel(dx, x.grad) < 1e-5 and _rel(dxp.float(), x.grad) < 2e-5
     assert _rel(dg, g.grad) < 1e-5 and _rel(db, b.grad) < 1e-5
     assert _rel(dbias, x.grad.sum(0)) < 1e-4
+    # the same backward as two launches: dx (+ planes) on the chain, the column sums trailing
+    dx2 = torch.empty(M, Cd, device="cuda")
+    dxp2 = L.Planes.empty(M, Cd, "cuda")
+    acc = torch.zeros(3, Cd, device="cuda")
+    L.layernorm_bwd_dx(dy, x.detach(), g.detach(), st, dx2, dxp2, M, Cd)
+    L.layernorm_bwd_cols(dy, x.detach(), st, acc[0], acc[1], M, Cd)
+    L.colsum_planes(dxp2, acc[2], accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx) and torch.equal(dxp2.float(), dxp.float())
+    assert _rel(acc[0], g.grad) < 1e-5 and _rel(acc[1], b.grad) < 1e-5 and _rel(acc[2], x.grad.sum(0)) < 1e-4
 
 
 @pytest.mark.parametrize("Tq,Tk", [(20, 288), (80, 80), (7, 36), (5, 12), (3, 1152), (2, 2048), (9, 50), (4, 130)])

@@ -109,8 +109,10 @@ def test_plain_bf16_mode_documented_looser_bound(golden_dir):
 
 
 def test_train_mode_dropout_statistics():
-    """Train-mode parity with the reference's Philox stream is impossible; check instead that
-    dropout is active, unbiased in expectation and reproducible for a fixed RNG state."""
+    """Train-mode parity with the reference's Philox stream is impossible; check instead that dropout is
+    active, reproducible for a fixed RNG state and re-drawn every forward.  (Keep rate 0.9 +- 0.01 and the exact 1/0.9
+    scaling of the kept elements -- i.e. unbiasedness -- are asserted at kernel level:
+    test_kernels_gpu.test_gemm_dropout_is_deterministic_and_unbiased.)"""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from yvb200 import ops

@@ -8,13 +8,14 @@
 // GEMM -> fp32 scores in HBM -> softmax kernel -> bf16 planes in HBM -> GEMM (3 launches forward, 6 backward).
 //
 // Work decomposition: one CTA per (128-query tile, head, pair); keys are streamed in chunks of 64.
-//   warps 8, 9 (one lane each): TMA producers and tcgen05.mma issuers.  Issuing a 128x64x16 MMA costs one thread about
+//   warps 16, 17 (one lane each): TMA producers and tcgen05.mma issuers.  Issuing a 128x64x16 MMA costs one thread about
 //                      60 cycles (descriptor moves to uniform registers), twice its tensor-pipe time, so the products
-//                      of a chunk are split over two issuing threads: forward S = Q K^T (warp 8, K double-buffered)
-//                      and O += P V (warp 9); backward S, dV^T (warp 8) and dPd, dK^T, dQ (warp 9).  Q (and dO) tiles
-//                      stay resident in shared memory, K / V chunks stream.
-//   warps 0-7        : softmax.  Warp w owns TMEM lanes 32*(w&3).. (query rows) and key columns 32*(w>>2).. of the
-//                      chunk: S comes out of TMEM with one tcgen05.ld.32x32b.x32, exp / dropout / hi-lo split run in
+//                      of a chunk are split over two issuing threads: forward S = Q K^T (first, K double-buffered)
+//                      and O += P V (second); backward S, dV^T and dPd, dK^T, dQ.  Q (and dO) tiles stay resident in
+//                      shared memory, K / V chunks stream.  (The kernels are templates on the softmax warp count;
+//                      YVB200_ATTN_WARPS=8 selects the 8-warp build, 32 keys per thread, for A/B timing.)
+//   warps 0-15       : softmax.  Warp w owns TMEM lanes 32*(w&3).. (query rows) and key columns 16*(w>>2).. of the
+//                      chunk: S comes out of TMEM with one tcgen05.ld.32x32b.x16, exp / dropout / hi-lo split run in
 //                      registers, P goes back to shared memory in the 128B-swizzled K-major operand layout and is the
 //                      A operand of the P V product (accumulated in TMEM across chunks, online-softmax rescaling of
 //                      the accumulator only when a row maximum grows by more than 8).
@@ -32,8 +33,9 @@ namespace {
 
 constexpr int QT = 128;            // query rows per CTA (UMMA M)
 constexpr int KC = 64;             // keys per chunk (UMMA N of the score product, one 128-byte swizzled row)
-constexpr int ATT_THREADS = 320;   // 8 softmax warps + 2 issuer warps (TMA + tcgen05.mma, one lane each)
-constexpr int SM_THREADS = 256;
+// SW softmax warps (8 or 16) + 2 issuer warps (TMA + tcgen05.mma, one lane each).  Softmax warp w owns TMEM lanes
+// 32 * (w & 3) .. (query rows) and the key columns [KPT * (w >> 2), +KPT) of a chunk, KPT = 64 / (SW / 4).
+constexpr int att_threads(int sw) { return sw * 32 + 64; }
 constexpr uint32_t Q_BLK = QT * 128;    // bytes of a [128 rows x 64 bf16] block
 constexpr uint32_t KV_BLK = KC * 128;   // bytes of a [64 rows x 64 bf16] block
 constexpr float RESCALE_THRESHOLD = 8.f;
@@ -84,10 +86,31 @@ YV_DEVINL void tmem_st32(uint32_t taddr, const uint32_t* v) {
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+YV_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+YV_DEVINL void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N> YV_DEVINL void tmem_ld(uint32_t taddr, uint32_t* v) { if (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v); }
+template <int N> YV_DEVINL void tmem_st(uint32_t taddr, const uint32_t* v) { if (N == 32) tmem_st32(taddr, v); else tmem_st16(taddr, v); }
 YV_DEVINL void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 YV_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 YV_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-YV_DEVINL void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int SW> YV_DEVINL void softmax_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SW * 32) : "memory"); }
 YV_DEVINL void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 YV_DEVINL uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -130,16 +153,16 @@ YV_DEVINL void mma_rows_x_rows(uint32_t tmem_d, uint32_t a_base, uint32_t a_blk,
                               desc_k(b_base + b * b_blk, s), desc_k(b_base + (DB + b) * b_blk, s), idesc, accum);
 }
 
-// the 32 keys [key0, key0 + 32) of query row `row` as an operand tile row: element (row, key) of a [128 x 64] block at
+// N consecutive keys (column group cg) of query row `row` as an operand tile row: element (row, key) of a [128 x 64] block at
 // row * 128 + ((key / 8) ^ (row % 8)) * 16 + (key % 8) * 2 (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B)
-template <int PASSES>
-YV_DEVINL void store_tile_row(uint32_t tile, int row, int half, const float* x) {
+template <int PASSES, int N>
+YV_DEVINL void store_tile_row(uint32_t tile, int row, int cg, const float* x) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < N / 8; ++g) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) yv_split2(x[8 * g + 2 * e], x[8 * g + 2 * e + 1], hi[e], lo[e]);
-        const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((4 * half + g) ^ (row & 7)) << 4);
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((N / 8) * cg + g) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
                      "r"(hi[3])
                      : "memory");
@@ -152,12 +175,12 @@ YV_DEVINL void store_tile_row(uint32_t tile, int row, int half, const float* x) 
 
 // Output tiles ([128 rows x DH], thread = row in registers) leave through a swizzled shared-memory staging area so that
 // the global stores are whole rows: 16-byte chunk c of row r of plane pl sits at pl * 128 * DH * 2 + r * DH * 2 +
-// ((c ^ (r & 7)) << 4).  stage_row32 writes 32 consecutive columns of one row, copy_out_rows writes the tile.
-template <int DH>
-YV_DEVINL void stage_row32(uint32_t stage, int row, int col0, const float* x) {
+// ((c ^ (r & 7)) << 4).  stage_row writes N consecutive columns of one row, copy_out_rows writes the tile.
+template <int DH, int N>
+YV_DEVINL void stage_row(uint32_t stage, int row, int col0, const float* x) {
     constexpr uint32_t ROW_B = DH * 2, PLANE_B = QT * ROW_B;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < N / 8; ++g) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) yv_split2(x[8 * g + 2 * e], x[8 * g + 2 * e + 1], hi[e], lo[e]);
@@ -170,7 +193,7 @@ YV_DEVINL void stage_row32(uint32_t stage, int row, int col0, const float* x) {
                      : "memory");
     }
 }
-template <int DH>
+template <int DH, int SW>
 YV_DEVINL void copy_out_rows(uint32_t stage, const PlaneView& out, long long grow0, int rows_valid, int head, int warp,
                              int lane) {
     constexpr uint32_t ROW_B = DH * 2, PLANE_B = QT * ROW_B;
@@ -178,7 +201,7 @@ YV_DEVINL void copy_out_rows(uint32_t stage, const PlaneView& out, long long gro
     constexpr int RPI = 32 / CPR;               // rows per warp instruction
     const int c = lane % CPR, rsub = lane / CPR;
 #pragma unroll 2
-    for (int r = warp * RPI + rsub; r < rows_valid; r += 8 * RPI) {
+    for (int r = warp * RPI + rsub; r < rows_valid; r += SW * RPI) {
         const uint32_t off = (uint32_t)r * ROW_B + (uint32_t)((c ^ (r & 7)) << 4);
         __nv_bfloat16* dst = out.ptr + (grow0 + r) * out.ld + head * DH + c * 8;
 #pragma unroll
@@ -191,19 +214,20 @@ YV_DEVINL void copy_out_rows(uint32_t stage, const PlaneView& out, long long gro
     }
 }
 
-// additive mask values of 32 consecutive keys, -inf past Tk (branch-free: clamped address, predicated select), issued
+// additive mask values of N consecutive keys, -inf past Tk (branch-free: clamped address, predicated select), issued
 // before the thread waits for the scores so that their latency is hidden behind the MMA
-YV_DEVINL void load_mask32(const float* mrow, int key0, int Tk, float* mk) {
+template <int N>
+YV_DEVINL void load_mask(const float* mrow, int key0, int Tk, float* mk) {
     if (mrow) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < N; ++i) {
             const int key = key0 + i;
             const float v = __ldg(mrow + min(key, Tk - 1));
             mk[i] = key < Tk ? v : -INFINITY;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mk[i] = (key0 + i) < Tk ? 0.f : -INFINITY;
+        for (int i = 0; i < N; ++i) mk[i] = (key0 + i) < Tk ? 0.f : -INFINITY;
     }
 }
 
@@ -211,7 +235,7 @@ template <int DH, int PASSES>
 struct FwdCfg {
     static constexpr int PL = PASSES == 3 ? 2 : 1;
     static constexpr int DB = DH / 64;
-    static constexpr uint32_t HEADER = 4096;                       // barriers, TMEM slot, row-statistic exchange
+    static constexpr uint32_t HEADER = 8192;                       // barriers, TMEM slot, row-statistic exchange
     static constexpr uint32_t SQ = 0;
     static constexpr uint32_t K_BUF = PL * DB * KV_BLK;             // one K chunk (all planes / head-dimension blocks)
     static constexpr uint32_t SK = SQ + PL * DB * Q_BLK;            // two K buffers
@@ -225,8 +249,8 @@ struct FwdCfg {
 };
 
 // ------------------------------------------------------------------------------------------- forward
-template <int DH, int PASSES>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int DH, int PASSES, int SW>
+__global__ void __launch_bounds__(att_threads(SW), 1)
 yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p) {
     using C = FwdCfg<DH, PASSES>;
@@ -236,8 +260,13 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     //           8 P written (+ O rescaled), 9 P V retired
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 96);
-    float* xm = reinterpret_cast<float*>(smem_raw + 128);           // [2 (chunk parity)][2 (column half)][128 rows]
-    float* xl = xm + 2 * 2 * QT;                                    // [2][128]
+    constexpr int CG = SW / 4;                                      // column groups per chunk
+    constexpr int KPT = KC / CG;                                    // keys per thread and chunk (32 or 16)
+    constexpr int OW = DH / CG;                                     // accumulator columns per softmax warp
+    constexpr int OG = OW < 32 ? OW : 32;                           // ... handled OG at a time
+    float* xm = reinterpret_cast<float*>(smem_raw + 128);           // [2 (chunk parity)][CG][128 rows]
+    float* xl = xm + 2 * CG * QT;                                   // [CG][128]
+    static_assert(128 + (3 * CG * QT) * 4 <= C::HEADER, "row-statistic exchange does not fit the header");
     const uint32_t tiles = (smem_u32(smem_raw) + C::HEADER + 1023u) & ~1023u;
     const uint32_t sQ = tiles + C::SQ, sK = tiles + C::SK, sV = tiles + C::SV, sP = tiles + C::SP;
     const uint32_t bar0 = smem_u32(bars);
@@ -257,16 +286,16 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         mbar_init(bar(B_V), 1);
         mbar_init(bar(B_S), 1);
         mbar_init(bar(B_S + 1), 1);
-        mbar_init(bar(B_SFREE), 8);
-        mbar_init(bar(B_SFREE + 1), 8);
-        mbar_init(bar(B_P), 8);
+        mbar_init(bar(B_SFREE), SW);
+        mbar_init(bar(B_SFREE + 1), SW);
+        mbar_init(bar(B_P), SW);
         mbar_init(bar(B_O), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_k) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_v) : "memory");
     }
-    if (warp == 8) {
+    if (warp == SW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(C::TMEM_COLS)
                      : "memory");
@@ -288,7 +317,7 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tma_load_5d(dst + (pl * DB + d) * KV_BLK, map, b, d * 64, chunk * KC, head, pair, pl);
     };
 
-    if (warp == 8) {
+    if (warp == SW) {
         if (lane == 0) {
             // ============================ Q / K loads, S = Q K^T (runs up to two chunks ahead) ============================
             mbar_expect_tx(bar(B_Q), PL * DB * Q_BLK);
@@ -319,7 +348,7 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 YV_AT(8 + 8 * c + 1);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == SW + 1) {
         if (lane == 0) {
             // ======================================= V loads, O += P V =======================================
             load_kv(&map_v, sV, bar(B_V), 0);
@@ -346,7 +375,7 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     } else {
         // ========================================= softmax ============================================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, cg = warp >> 2;
         const int row = quarter * 32 + lane;                  // row of the tile = TMEM lane
         const int qrow = q0 + row;
         const bool row_ok = qrow < p.Tq;
@@ -356,45 +385,46 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const float* mrow = p.mask ? p.mask + (long long)pair * p.Tk : nullptr;
         float m_ref = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nchunks; ++j) {
-            const int key0 = j * KC + half * 32;
-            float x[32];
-            load_mask32(mrow, key0, p.Tk, x);
+            const int key0 = j * KC + cg * KPT;
+            float x[KPT];
+            load_mask<KPT>(mrow, key0, p.Tk, x);
             mbar_wait(bar(B_S + (j & 1)), (uint32_t)((j >> 1) & 1));
             if (threadIdx.x == 0) YV_AT(8 + 8 * j + 4);
             tc_fence_after();
-            uint32_t raw[32];
-            tmem_ld32(tmem + lane_addr + (uint32_t)((j & 1) * KC + half * 32), raw);
+            uint32_t raw[KPT];
+            tmem_ld<KPT>(tmem + lane_addr + (uint32_t)((j & 1) * KC + cg * KPT), raw);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_SFREE + (j & 1)));       // this S buffer may take chunk j + 2
             if (threadIdx.x == 0) YV_AT(64 + 8 * j + 0);
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < KPT; ++i) {
                 x[i] = fmaf(__uint_as_float(raw[i]), p.scale, x[i]);      // -inf for keys past Tk
                 mx = fmaxf(mx, x[i]);
             }
-            float* xmj = xm + (j & 1) * 2 * QT;
-            xmj[half * QT + row] = mx;
+            float* xmj = xm + (j & 1) * CG * QT;
+            xmj[cg * QT + row] = mx;
             if (threadIdx.x == 0) YV_AT(64 + 8 * j + 1);
-            softmax_bar();
-            mx = fmaxf(mx, xmj[(half ^ 1) * QT + row]);
+            softmax_bar<SW>();
+#pragma unroll
+            for (int g = 0; g < CG; ++g) mx = fmaxf(mx, xmj[g * QT + row]);
             if (threadIdx.x == 0) YV_AT(8 + 8 * j + 5);
             // online softmax with a lazy reference maximum: the accumulator is rescaled only when the row maximum
-            // grew by more than RESCALE_THRESHOLD (both column halves take the same decision from the same numbers)
+            // grew by more than RESCALE_THRESHOLD (all column groups take the same decision from the same numbers)
             const float m_new = (j == 0 || mx > m_ref + RESCALE_THRESHOLD) ? mx : m_ref;
             const float alpha = (j == 0) ? 1.f : __expf(m_ref - m_new);
             m_ref = m_new;
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < KPT; ++i) {
                 x[i] = __expf(x[i] - m_new);                  // exp(-inf) = 0 for keys past Tk
                 sum += x[i];
             }
             l_run = l_run * alpha + sum;
             if (drop.thresh) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] *= yv_drop_mul(drop, drop_row + (uint32_t)(key0 + i));
+                for (int i = 0; i < KPT; ++i) x[i] *= yv_drop_mul(drop, drop_row + (uint32_t)(key0 + i));
             }
             if (threadIdx.x == 0) YV_AT(8 + 8 * j + 6);
             if (j > 0) {
@@ -402,18 +432,18 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
-                    for (int g = 0; g < DH / 64; ++g) {
-                        uint32_t o[32];
-                        const uint32_t a = tmem_o + lane_addr + (uint32_t)(half * (DH / 2) + g * 32);
-                        tmem_ld32(a, o);
+                    for (int g = 0; g < OW / OG; ++g) {
+                        uint32_t o[OG];
+                        const uint32_t a = tmem_o + lane_addr + (uint32_t)(cg * OW + g * OG);
+                        tmem_ld<OG>(a, o);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(a, o);
+                        for (int i = 0; i < OG; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st<OG>(a, o);
                     }
                 }
             }
             if (threadIdx.x == 0) YV_AT(64 + 8 * j + 2);
-            store_tile_row<PASSES>(sP, row, half, x);
+            store_tile_row<PASSES, KPT>(sP, row, cg, x);
             if (threadIdx.x == 0) YV_AT(64 + 8 * j + 3);
             fence_async_smem();
             tc_fence_before();
@@ -426,43 +456,46 @@ yv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         mbar_wait(bar(B_O), (uint32_t)((nchunks - 1) & 1));
         if (threadIdx.x == 0) YV_AT(2);
         tc_fence_after();
-        xl[half * QT + row] = l_run;
-        softmax_bar();
-        const float l_tot = l_run + xl[(half ^ 1) * QT + row];
+        xl[cg * QT + row] = l_run;
+        softmax_bar<SW>();
+        float l_tot = 0.f;
+#pragma unroll
+        for (int g = 0; g < CG; ++g) l_tot += xl[g * QT + row];
         const float inv = 1.f / l_tot;
         const long long grow = (long long)pair * p.Tq + qrow;
 #pragma unroll 1
-        for (int g = 0; g < DH / 64; ++g) {
-            uint32_t o[32];
-            const int col = half * (DH / 2) + g * 32;
-            tmem_ld32(tmem_o + lane_addr + (uint32_t)col, o);
-            float y[32];
+        for (int g = 0; g < OW / OG; ++g) {
+            uint32_t o[OG];
+            const int col = cg * OW + g * OG;
+            tmem_ld<OG>(tmem_o + lane_addr + (uint32_t)col, o);
+            float y[OG];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]) * inv;
-            stage_row32<DH>(tiles, row, col, y);
+            for (int i = 0; i < OG; ++i) y[i] = __uint_as_float(o[i]) * inv;
+            stage_row<DH, OG>(tiles, row, col, y);
             if (p.o32 && row_ok) {
                 float* dst32 = p.o32 + grow * p.o32_ld + head * DH + col;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < OG / 4; ++i)
                     *reinterpret_cast<float4*>(dst32 + 4 * i) = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
             }
         }
-        if (half == 0 && row_ok && p.lse) p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow] = m_ref + logf(l_tot);
-        softmax_bar();
-        copy_out_rows<DH>(tiles, p.o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
+        if (cg == 0 && row_ok && p.lse) p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow] = m_ref + logf(l_tot);
+        softmax_bar<SW>();
+        copy_out_rows<DH, SW>(tiles, p.o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
         if (threadIdx.x == 0) YV_AT(3);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 8)
+    if (warp == SW)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
 }
 
 // dK / dV planes of one (pair, head) = sum over the query tiles' slabs.  NS > 0: slab count known at compile time, all
 // NS * UNR loads of a batch are issued before the first add (the last CTA of a (pair, head) runs this alone).
-template <int DH, int NS>
+template <int DH, int NS, int SW>
 YV_DEVINL void sum_slabs(const AttnParams& p, int pair, int head, int nslabs) {
+    constexpr int SM_THREADS = SW * 32;
     constexpr int V4 = DH / 4;
     constexpr int UNR = NS == 1 ? 8 : 4;
     const long long slab_stride = (long long)p.pairs * p.Tk * p.dkv_ld;
@@ -547,13 +580,13 @@ struct BwdCfg {
 
 // delta[r] = sum_d dO[r, d] * O[r, d] (the softmax-backward row term) for the 128 rows of a query tile, from the global
 // plane pairs: a warp reads whole rows (8 bytes per lane and plane, coalesced), four rows in flight, shuffle reduction
-template <int DH>
+template <int DH, int SW>
 YV_DEVINL void row_dots(const PlaneView& a, const PlaneView& b, long long grow0, int rows_valid, int head, int warp, int lane,
                         float* delta) {
     constexpr int LPR = DH / 4;                 // lanes per row (4 bf16 = 8 bytes each)
     constexpr int RPI = 32 / LPR;               // rows per warp instruction (1 for DH = 128, 2 for DH = 64)
     const int c = (lane % LPR) * 4, rsub = lane / LPR;
-    for (int r0 = warp * RPI * 4; r0 < QT; r0 += 8 * RPI * 4) {
+    for (int r0 = warp * RPI * 4; r0 < QT; r0 += SW * RPI * 4) {
         uint2 ah[4], al[4], bh[4], bl[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -587,8 +620,8 @@ YV_DEVINL void row_dots(const PlaneView& a, const PlaneView& b, long long grow0,
     }
 }
 
-template <int DH, int PASSES>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int DH, int PASSES, int SW>
+__global__ void __launch_bounds__(att_threads(SW), 1)
 yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
                    const __grid_constant__ AttnParams p) {
@@ -602,6 +635,10 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint32_t* last_flag = reinterpret_cast<uint32_t*>(smem_raw + 68);
     float* delta_s = reinterpret_cast<float*>(smem_raw + 256);      // [128] row terms dO . O
     constexpr int B_QDO = 0, B_KV = 1, B_S = 2, B_DP = 3, B_T = 4, B_DV = 5, B_DKQ = 6;
+    constexpr int CG = SW / 4;                                      // column groups per chunk
+    constexpr int KPT = KC / CG;                                    // keys per thread and chunk (32 or 16)
+    constexpr int OW = DH / CG;                                     // dQ columns per softmax warp
+    constexpr int OG = OW < 32 ? OW : 32;
     const uint32_t tiles = (smem_u32(smem_raw) + C::HEADER + 1023u) & ~1023u;
     const uint32_t sQ = tiles + C::SQ, sDO = tiles + C::SDO, sK = tiles + C::SK, sV = tiles + C::SV, sT = tiles + C::ST,
                    sD = tiles + C::SD;
@@ -619,7 +656,7 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         mbar_init(bar(B_KV), 1);
         mbar_init(bar(B_S), 1);
         mbar_init(bar(B_DP), 1);
-        mbar_init(bar(B_T), 8);
+        mbar_init(bar(B_T), SW);
         mbar_init(bar(B_DV), 1);
         mbar_init(bar(B_DKQ), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -628,7 +665,7 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_v) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&map_do) : "memory");
     }
-    if (warp == 8) {
+    if (warp == SW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(C::TMEM_COLS)
                      : "memory");
@@ -642,7 +679,7 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     yv_pdl_wait();
 
     const uint32_t idesc_t = make_idesc(128, KC, 1, 1);          // dV^T / dK^T: both operands MN-major
-    if (warp == 8) {
+    if (warp == SW) {
         if (lane == 0) {
             // =========================== loads, S = Q K^T, dV^T = dO^T Pd ===========================
             auto load_rows = [&](const CUtensorMap* map, uint32_t dst, uint32_t blk, uint32_t b, int row0) {
@@ -690,7 +727,7 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == SW + 1) {
         if (lane == 0) {
             // =========================== dPd = dO V^T, dK^T = Q^T dS, dQ += dS K ===========================
             const uint32_t idesc_dq = make_idesc(QT, DH, 0, 1);
@@ -725,7 +762,7 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     } else {
         // ========================================= softmax ============================================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, cg = warp >> 2;
         const int row = quarter * 32 + lane;
         const int qrow = q0 + row;
         const bool row_ok = qrow < p.Tq;
@@ -733,34 +770,33 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const YvDrop drop = yv_drop_make(p.rng, p.drop_site, p.drop_p);
         const uint32_t drop_row = (uint32_t)(((long long)(pair * p.heads + head) * p.Tq + qrow) * p.Tk);
         const float* mrow = p.mask ? p.mask + (long long)pair * p.Tk : nullptr;
-        const long long grow = (long long)pair * p.Tq + qrow;
         // rows past Tq (zero-filled by TMA) get lse = +inf: their probabilities and dS are exactly zero
-        row_dots<DH>(p.d_o, p.fwd_o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane, delta_s);
+        row_dots<DH, SW>(p.d_o, p.fwd_o, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane, delta_s);
         const float lse = row_ok ? p.lse[(long long)(pair * p.heads + head) * p.Tq + qrow] : INFINITY;
-        softmax_bar();
+        softmax_bar<SW>();
         const float delta = delta_s[row];
         // partial dK / dV of this query tile: slab `qtile` of the workspace, lane = head dimension index
         const int d_lane = quarter * 32 + lane;
         float* slab = p.dkv32 + ((long long)qtile * p.pairs + pair) * p.Tk * p.dkv_ld + head * DH + d_lane;
         for (int j = 0; j < nchunks; ++j) {
             const uint32_t ph = (uint32_t)(j & 1);
-            const int key0 = j * KC + half * 32;
-            float pd[32], ds[32];
-            load_mask32(mrow, key0, p.Tk, pd);
+            const int key0 = j * KC + cg * KPT;
+            float pd[KPT], ds[KPT];
+            load_mask<KPT>(mrow, key0, p.Tk, pd);
             mbar_wait(bar(B_S), ph);
             if (threadIdx.x == 0) YV_AT(8 + 16 * j + 8);
             tc_fence_after();
             {
-                uint32_t raw[32];
-                tmem_ld32(tm_s + lane_addr + (uint32_t)(half * 32), raw);
+                uint32_t raw[KPT];
+                tmem_ld<KPT>(tm_s + lane_addr + (uint32_t)(cg * KPT), raw);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
+                for (int i = 0; i < KPT; ++i)
                     pd[i] = __expf(fmaf(__uint_as_float(raw[i]), p.scale, pd[i]) - lse);   // 0 past Tk / past Tq
                 mbar_wait(bar(B_DP), ph);
                 tc_fence_after();
-                tmem_ld32(tm_dp + lane_addr + (uint32_t)(half * 32), raw);
+                tmem_ld<KPT>(tm_dp + lane_addr + (uint32_t)(cg * KPT), raw);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < KPT; ++i) {
                     const float mult = drop.thresh ? yv_drop_mul(drop, drop_row + (uint32_t)(key0 + i)) : 1.f;
                     const float pr = pd[i];
                     ds[i] = p.scale * pr * (__uint_as_float(raw[i]) * mult - delta);
@@ -769,28 +805,28 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             }
             if (threadIdx.x == 0) YV_AT(8 + 16 * j + 9);
             // (the products that read the previous chunk's tiles retired before this thread drained their results)
-            store_tile_row<PASSES>(sT, row, half, pd);
-            store_tile_row<PASSES>(sD, row, half, ds);
+            store_tile_row<PASSES, KPT>(sT, row, cg, pd);
+            store_tile_row<PASSES, KPT>(sD, row, cg, ds);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_T));
             if (threadIdx.x == 0) YV_AT(8 + 16 * j + 10);
             // drain dV^T and dK^T (lane = d, column = key): 128-byte coalesced rows of the slab
-            const int nkeys = min(32, p.Tk - key0);               // warp-uniform
+            const int nkeys = min(KPT, p.Tk - key0);              // warp-uniform
             mbar_wait(bar(B_DV), ph);
             if (threadIdx.x == 0) YV_AT(8 + 16 * j + 11);
             tc_fence_after();
             if (DH == 128 || quarter < 2) {
-                uint32_t raw[32];
-                tmem_ld32(tm_dv + lane_addr + (uint32_t)(half * 32), raw);
+                uint32_t raw[KPT];
+                tmem_ld<KPT>(tm_dv + lane_addr + (uint32_t)(cg * KPT), raw);
                 float* dst = slab + (long long)key0 * p.dkv_ld + p.dv_col;
-                if (nkeys >= 32) {
+                if (nkeys >= KPT) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                    for (int i = 0; i < KPT; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
+                    for (int i = 0; i < KPT; ++i)
                         if (i < nkeys) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
                 }
             }
@@ -799,15 +835,15 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             if (threadIdx.x == 0) YV_AT(8 + 16 * j + 13);
             tc_fence_after();
             if (DH == 128 || quarter < 2) {
-                uint32_t raw[32];
-                tmem_ld32(tm_dk + lane_addr + (uint32_t)(half * 32), raw);
+                uint32_t raw[KPT];
+                tmem_ld<KPT>(tm_dk + lane_addr + (uint32_t)(cg * KPT), raw);
                 float* dst = slab + (long long)key0 * p.dkv_ld + p.dk_col;
-                if (nkeys >= 32) {
+                if (nkeys >= KPT) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
+                    for (int i = 0; i < KPT; ++i) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
+                    for (int i = 0; i < KPT; ++i)
                         if (i < nkeys) dst[(long long)i * p.dkv_ld] = __uint_as_float(raw[i]);
                 }
             }
@@ -817,19 +853,19 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (threadIdx.x == 0) YV_AT(1);
         // ---- dQ tile -> planes through the (now free) operand tiles
 #pragma unroll 1
-        for (int g = 0; g < DH / 64; ++g) {
-            uint32_t o[32];
-            const int col = half * (DH / 2) + g * 32;
-            tmem_ld32(tm_dq + lane_addr + (uint32_t)col, o);
-            float y[32];
+        for (int g = 0; g < OW / OG; ++g) {
+            uint32_t o[OG];
+            const int col = cg * OW + g * OG;
+            tmem_ld<OG>(tm_dq + lane_addr + (uint32_t)col, o);
+            float y[OG];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(o[i]);
-            stage_row32<DH>(tiles, row, col, y);
+            for (int i = 0; i < OG; ++i) y[i] = __uint_as_float(o[i]);
+            stage_row<DH, OG>(tiles, row, col, y);
         }
         __threadfence();                                      // this tile's slab is visible before the ticket is taken
-        softmax_bar();
+        softmax_bar<SW>();
         if (threadIdx.x == 0) YV_AT(2);
-        copy_out_rows<DH>(tiles, p.dq, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
+        copy_out_rows<DH, SW>(tiles, p.dq, (long long)pair * p.Tq + q0, min(QT, p.Tq - q0), head, warp, lane);
         // ---- the last query tile of this (pair, head) adds the slabs and writes the dK / dV planes
         if (threadIdx.x == 0) {
             const unsigned t = atomicAdd(p.tickets + pair * p.heads + head, 1u);
@@ -837,22 +873,22 @@ yv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             if (last) p.tickets[pair * p.heads + head] = 0u;  // self-resetting: the buffer can be reused by the next launch
             *last_flag = last ? 1u : 0u;
         }
-        softmax_bar();
+        softmax_bar<SW>();
         if (threadIdx.x == 0) YV_AT(3);
         if (*last_flag) {
             __threadfence();
             const int nslabs = (int)gridDim.x;
-            if (nslabs == 1) sum_slabs<DH, 1>(p, pair, head, 1);
-            else if (nslabs == 2) sum_slabs<DH, 2>(p, pair, head, 2);
-            else if (nslabs == 3) sum_slabs<DH, 3>(p, pair, head, 3);
-            else sum_slabs<DH, 0>(p, pair, head, nslabs);
+            if (nslabs == 1) sum_slabs<DH, 1, SW>(p, pair, head, 1);
+            else if (nslabs == 2) sum_slabs<DH, 2, SW>(p, pair, head, 2);
+            else if (nslabs == 3) sum_slabs<DH, 3, SW>(p, pair, head, 3);
+            else sum_slabs<DH, 0, SW>(p, pair, head, nslabs);
         }
     }
 
     if (threadIdx.x == 0) YV_AT(4);
     tc_fence_before();
     __syncthreads();
-    if (warp == 8)
+    if (warp == SW)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
 }
 
@@ -894,7 +930,10 @@ int set_smem_once(K kernel, int bytes, bool (&done)[64], std::mutex& mu) {
     return 0;
 }
 
-template <int DH, int PASSES>
+// softmax warps per CTA: 16 by default, YVB200_ATTN_WARPS=8 selects the 8-warp build (A/B timing)
+const int g_attn_warps = []() { const char* e = getenv("YVB200_ATTN_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+
+template <int DH, int PASSES, int SW>
 int launch_fwd(const YvAttnFwd* a, const AttnParams& p, cudaStream_t st) {
     using C = FwdCfg<DH, PASSES>;
     CUtensorMap mq, mk, mv;
@@ -903,13 +942,13 @@ int launch_fwd(const YvAttnFwd* a, const AttnParams& p, cudaStream_t st) {
     if (view_map(&mv, a->v, a->pairs, a->heads, DH, PASSES, KC, "V")) return 1;
     static bool done[64] = {};
     static std::mutex mu;
-    if (set_smem_once(yv_attn_fwd_kernel<DH, PASSES>, (int)C::SMEM, done, mu)) return 2;
+    if (set_smem_once(yv_attn_fwd_kernel<DH, PASSES, SW>, (int)C::SMEM, done, mu)) return 2;
     dim3 grid((unsigned)((p.Tq + QT - 1) / QT), (unsigned)a->heads, (unsigned)a->pairs);
-    YV_CUDA(yv_launch(yv_attn_fwd_kernel<DH, PASSES>, grid, dim3(ATT_THREADS), C::SMEM, st, mq, mk, mv, p));
+    YV_CUDA(yv_launch(yv_attn_fwd_kernel<DH, PASSES, SW>, grid, dim3(att_threads(SW)), C::SMEM, st, mq, mk, mv, p));
     return 0;
 }
 
-template <int DH, int PASSES>
+template <int DH, int PASSES, int SW>
 int launch_bwd(const YvAttnBwd* a, const AttnParams& p, cudaStream_t st) {
     using C = BwdCfg<DH, PASSES>;
     CUtensorMap mq, mk, mv, md;
@@ -919,9 +958,9 @@ int launch_bwd(const YvAttnBwd* a, const AttnParams& p, cudaStream_t st) {
     if (view_map(&md, a->dout, a->pairs, a->heads, DH, PASSES, QT, "dO")) return 1;
     static bool done[64] = {};
     static std::mutex mu;
-    if (set_smem_once(yv_attn_bwd_kernel<DH, PASSES>, (int)C::SMEM, done, mu)) return 2;
+    if (set_smem_once(yv_attn_bwd_kernel<DH, PASSES, SW>, (int)C::SMEM, done, mu)) return 2;
     dim3 grid((unsigned)((p.Tq + QT - 1) / QT), (unsigned)a->heads, (unsigned)a->pairs);
-    YV_CUDA(yv_launch(yv_attn_bwd_kernel<DH, PASSES>, grid, dim3(ATT_THREADS), C::SMEM, st, mq, mk, mv, md, p));
+    YV_CUDA(yv_launch(yv_attn_bwd_kernel<DH, PASSES, SW>, grid, dim3(att_threads(SW)), C::SMEM, st, mq, mk, mv, md, p));
     return 0;
 }
 
@@ -968,8 +1007,13 @@ extern "C" int yv_attn_fwd(const YvAttnFwd* a, yv_stream_t stream) {
     p.lse = a->lse;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;
-    if (a->dh == 128) rc = a->passes == 3 ? launch_fwd<128, 3>(a, p, st) : launch_fwd<128, 1>(a, p, st);
-    else rc = a->passes == 3 ? launch_fwd<64, 3>(a, p, st) : launch_fwd<64, 1>(a, p, st);
+    if (g_attn_warps == 16) {
+        if (a->dh == 128) rc = a->passes == 3 ? launch_fwd<128, 3, 16>(a, p, st) : launch_fwd<128, 1, 16>(a, p, st);
+        else rc = a->passes == 3 ? launch_fwd<64, 3, 16>(a, p, st) : launch_fwd<64, 1, 16>(a, p, st);
+    } else {
+        if (a->dh == 128) rc = a->passes == 3 ? launch_fwd<128, 3, 8>(a, p, st) : launch_fwd<128, 1, 8>(a, p, st);
+        else rc = a->passes == 3 ? launch_fwd<64, 3, 8>(a, p, st) : launch_fwd<64, 1, 8>(a, p, st);
+    }
     if (rc) return rc;
     YV_CUDA(cudaGetLastError());
     yv_count_launch();
@@ -1019,8 +1063,13 @@ extern "C" int yv_attn_bwd(const YvAttnBwd* a, yv_stream_t stream) {
     p.tickets = a->tickets;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;
-    if (a->dh == 128) rc = a->passes == 3 ? launch_bwd<128, 3>(a, p, st) : launch_bwd<128, 1>(a, p, st);
-    else rc = a->passes == 3 ? launch_bwd<64, 3>(a, p, st) : launch_bwd<64, 1>(a, p, st);
+    if (g_attn_warps == 16) {
+        if (a->dh == 128) rc = a->passes == 3 ? launch_bwd<128, 3, 16>(a, p, st) : launch_bwd<128, 1, 16>(a, p, st);
+        else rc = a->passes == 3 ? launch_bwd<64, 3, 16>(a, p, st) : launch_bwd<64, 1, 16>(a, p, st);
+    } else {
+        if (a->dh == 128) rc = a->passes == 3 ? launch_bwd<128, 3, 8>(a, p, st) : launch_bwd<128, 1, 8>(a, p, st);
+        else rc = a->passes == 3 ? launch_bwd<64, 3, 8>(a, p, st) : launch_bwd<64, 1, 8>(a, p, st);
+    }
     if (rc) return rc;
     YV_CUDA(cudaGetLastError());
     yv_count_launch();
