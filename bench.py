@@ -340,8 +340,8 @@ def main():
               "pairs_per_gpu": pairs, "global_batch": pairs * world, "parallelism": f"dp{a.gpus}", "precision": a.precision,
               "train_gflop_per_pair": train_gflop_per_pair,
               "gradient_exchange": "none (1 GPU)" if world == 1 else
-              "segments closed by external CUDA events inside the step graph; grouped NCCL all-reduce per segment on a "
-              "communication stream while the rest of backward runs",
+              "segments closed by external CUDA events inside the step graph; each segment's slice of one flat buffer is "
+              "averaged on a communication stream while the rest of backward runs",
               "l2": "flushed between timed steps (256 MB write); per-step working set ~3 GB >> 126 MB L2"}
 
     if a.impl == "reference":
@@ -421,7 +421,7 @@ def main():
     metrics = {k: {t: float(v) for t, v in d.items()} for k, d in step.metrics().items()}   # one packed all-reduce
 
     t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    exchange_check = None
+    exchange_check = exchange_mean_error = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # after the exchange every rank must hold the same averaged gradients (ranks see different batches)
@@ -430,6 +430,8 @@ def main():
         allc = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         exchange_check = float(max(((c - allc[0]).abs() / allc[0].clamp_min(1e-30)).max() for c in allc))
+        exchange_mean_error = exchange.verify()      # vs all-gather + fp64 mean of the ranks' local gradients
+        config["gradient_exchange"] += f" [transport: {exchange.transport}, payload: {exchange.payload}]"
     t_dev, t_e2e = float(t[0]), float(t[1])
     if world > 1:
         dist.barrier()
@@ -443,7 +445,8 @@ def main():
         print(json.dumps({"quick": True, "workload": a.workload, "ms_per_step": ms_per_step,
                           "e2e_ms_per_step": t_e2e / a.steps * 1e3, "value": value,
                           "gpu_launches_per_step": step.launches_per_step, "final_loss": final_loss,
-                          "exchange_max_rank_mismatch": exchange_check,
+                          "exchange_max_rank_mismatch": exchange_check, "exchange_mean_error": exchange_mean_error,
+                          "exchange_transport": getattr(exchange, "transport", None),
                           "variant": os.environ.get("YVB200_GEMM_VARIANT", "auto")}))
         return
 
@@ -501,7 +504,8 @@ def main():
             "gpu_launches": step.launches_per_step * a.steps, "gpu_launches_per_step": step.launches_per_step,
             "cuda_graph": not a.no_graph, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "torch_ops_on_gpu_proxy": torch_gpu, "fused_adamw_ms_per_step": optim_ms,
-            "exchange_max_rank_mismatch": exchange_check, "train_tflops_algorithmic": value * train_gflop_per_pair / 1e3,
+            "exchange_max_rank_mismatch": exchange_check, "exchange_mean_error": exchange_mean_error,
+            "train_tflops_algorithmic": value * train_gflop_per_pair / 1e3,
             "final_loss": final_loss, "step_metrics": metrics, "parity_check": parity}
     print(json.dumps(line))
 

@@ -245,6 +245,12 @@ int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out
               yv_stream_t stream);
 int yv_colsum_planes(const void* planes, int64_t ld, int64_t plane_stride, int64_t rows, int32_t cols,
                      float* out, int32_t accumulate, yv_stream_t stream);
+/* Gradient exchange over peer-to-peer copies (the reference gets its averaging from DistributedDataParallel's NCCL
+ * all-reduce, utils/distributed.py:97-99): mean over the ranks, summed in rank order, of one chunk of the flat gradient
+ * buffer.  `own` = this rank's copy of the chunk (overwritten with the mean); row step-1 of `stage` (rows `stage_stride`
+ * floats apart) = the copy pulled from rank (rank - step) mod world, step = 1..world-1.  n floats, a multiple of 4. */
+int yv_mean_chunks(float* own, const float* stage, int64_t stage_stride, int32_t world, int32_t rank, int64_t n,
+                   yv_stream_t stream);
 /* backward of the GEMM-epilogue activations when the upstream gradient arrives as f32:
  * planes = dy * act'(aux)  (GELU: aux = saved pre-activation, vilbert/vilbert.py:113-119; ReLU: aux = output) */
 int yv_act_bwd_split(const float* dy, int64_t ld_dy, const float* aux, int64_t ld_aux, int32_t act, void* planes,

@@ -563,3 +563,56 @@ def test_two_devices_in_one_process():
         if float(g0[n].norm()) < 1e-6 * gmax:
             continue
         assert float((g0[n] - g1[n]).norm()) < 1e-4 * float(g0[n].norm()) + 1e-6 * gmax, n
+
+
+def test_exchange_plan_writes_weight_gradients_in_place():
+    """GradientExchange on a one-rank NCCL group around the captured cfg2 step: after the observed first pass the
+    weight-gradient GEMMs write straight into the flat exchange buffer (``ops._dw_out``), so almost no gradient byte is
+    copied before the collective -- and the gradients are those of the same step without an exchange."""
+    _need_gpu()
+    import socket
+    import torch.distributed as dist
+    from yvb200 import ops
+    from yvb200.step import GradientExchange, GraphedStep
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        wl = "cfg2"
+        cfg = synth.CONFIGS[synth.WORKLOADS[wl]["config"]]
+        args = synth.workload_args(wl)
+        batch = synth.make_batch(wl, seed=5)
+        r = ops.rt("cuda")
+        model = build_lily(cfg, args, device="cuda").eval()          # eval: no dropout, both steps see the same function
+        plain = GraphedStep(model, args, batch, use_graph=True)
+        plain.run()
+        torch.cuda.synchronize()
+        want = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        del plain
+        ex = GradientExchange(model, segment_mb=64, direct=True)
+        step = GraphedStep(model, args, batch, use_graph=True, exchange=ex)
+        assert ex.plan is not None and ex._pass_plan is ex.plan and len(ex.segments) > 4
+        assert len(r.grad_sink) > 50
+        assert ex.in_place_fraction() > 0.8, ex.in_place_fraction()
+        for _ in range(2):
+            step.run()
+        torch.cuda.synchronize()
+        bucket = ex.plan.bucket.untyped_storage().data_ptr()
+        gmax = max(float(v.norm()) for v in want.values())
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            assert p.grad.untyped_storage().data_ptr() == bucket, n      # averaged gradients are views of the flat buffer
+            if float(want[n].norm()) < 1e-6 * gmax:
+                continue
+            bad = float((p.grad - want[n]).norm()) / (float(want[n].norm()) + 1e-2 * gmax)
+            assert bad < 1e-4, (n, bad, [n2 for n2, p2 in model.named_parameters() if p2.grad is not None and
+                                         float((p2.grad - want[n2]).norm()) > 1e-4 * float(want[n2].norm()) + 1e-6 * gmax][:40])
+        ex.remove()
+        assert not r.grad_sink
+    finally:
+        dist.destroy_process_group()

@@ -55,6 +55,34 @@ def _worker(rank, world, port, q):
     err_a = max(float((p.grad - want[n]).abs().max() / (want[n].abs().max() + 1e-12))
                 for n, p in m1.named_parameters() if p.grad is not None)
     n_buckets = ex.launched
+    # second pass: the layout frozen after the first pass is followed (fixed views of one flat buffer per gradient)
+    planned = ex.plan is not None
+    m1.zero_grad()
+    out = m1(*synth.model_inputs(batches[rank]))
+    ex.begin()
+    losses.total_loss(losses.step_losses(batches[rank], out, args, True), args).backward()
+    ex.end()
+    planned = planned and ex._pass_plan is ex.plan and len(ex.segments) * 2 == n_buckets * 2
+    ex.exchange()
+    err_a = max(err_a, max(float((p.grad - want[n]).abs().max() / (want[n].abs().max() + 1e-12))
+                           for n, p in m1.named_parameters() if p.grad is not None))
+    views = {id(v.untyped_storage()) for vs in ex.plan.views for v in vs} if planned else set()
+    planned = planned and len(views) == 1 and all(p.grad.untyped_storage().data_ptr() == ex.plan.bucket.untyped_storage().data_ptr()
+                                                  for p in m1.parameters() if p.grad is not None)
+    # third pass with a parameter frozen: the arrival order no longer matches, the pass is observed and re-planned
+    frozen = next(p for n, p in m1.named_parameters() if n.endswith("v_layer.0.attention.self.query.weight"))
+    frozen.requires_grad_(False)
+    m1.zero_grad()
+    out = m1(*synth.model_inputs(batches[rank]))
+    ex.begin()
+    losses.total_loss(losses.step_losses(batches[rank], out, args, True), args).backward()
+    ex.end()
+    replanned = ex._pass_plan is None and ex.plan is not None and all(q is not frozen for q in ex.plan.order)
+    ex.exchange()
+    err_a = max(err_a, max(float((p.grad - want[n]).abs().max() / (want[n].abs().max() + 1e-12))
+                           for n, p in m1.named_parameters() if p.grad is not None))
+    if not (planned and replanned):
+        err_a = float("inf")
     ex.remove()
 
     # (b) the reference's wrapper

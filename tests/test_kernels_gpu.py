@@ -377,3 +377,21 @@ def test_gemm_split_k_linear_epilogue(L, shape):
     # MN-major operands (wgrad form) through the same path
     out, _, _ = _run_gemm(L, A, B, True, True, 3)
     assert _rel(out, A.double() @ B.double().t()) < 3e-5
+
+
+@pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (8, 3), (5, 4)])
+def test_mean_chunks_matches_rank_ordered_sum(L, world, rank):
+    """Chunk mean of the copy-engine gradient exchange: bit-identical to summing the ranks' copies in rank order."""
+    from yvb200.step import GradientExchange as GE
+    n = 4 * 1237
+    torch.manual_seed(world * 10 + rank)
+    stage = torch.randn(world - 1, n + 64, device="cuda")
+    own = torch.randn(n, device="cuda")
+    want = torch.cat([own.clone(), torch.zeros(0, device="cuda")])
+    sl = torch.zeros(world * n, device="cuda")
+    sl[rank * n:(rank + 1) * n] = own
+    GE.ce_reduce(rank, world, sl, n, stage[:, :n])
+    want = sl[rank * n:(rank + 1) * n]
+    L.mean_chunks(own, stage, world, rank)
+    torch.cuda.synchronize()
+    assert torch.equal(own, want)

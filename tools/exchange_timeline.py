@@ -46,7 +46,11 @@ def main():
     warm = torch.ones(1, device=dev)
     dist.all_reduce(warm)
     torch.cuda.synchronize()
-    ex = GradientExchange(model)
+    spec = (sys.argv[1] if len(sys.argv) > 1 else "nccl:320").split(":")      # transport : largest MB [: smallest MB]
+    os.environ["YVB200_EXCHANGE"] = spec[0]
+    ex = GradientExchange(model, segment_mb=float(spec[1]) if len(spec) > 1 else None)
+    if len(spec) > 2:
+        ex.segment_min_bytes = int(float(spec[2]) * 2 ** 20)
     st = GraphedStep(model, args, batch, use_graph=True, exchange=ex)
     for _ in range(4):
         st.run()
@@ -60,11 +64,17 @@ def main():
         os.makedirs(os.path.dirname(out), exist_ok=True)
         prof.export_chrome_trace(out)
         ev = json.load(open(out))["traceEvents"]
-        ks = sorted((e for e in ev if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+        ks = sorted((e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy")), key=lambda e: e["ts"])
         os.remove(out)
         t0 = ks[0]["ts"]
-        nccl = [e for e in ks if "nccl" in e["name"].lower()]
-        comp = [e for e in ks if "nccl" not in e["name"].lower()]
+        # communication = NCCL kernels, or (copy-engine transport) everything on the streams that carry peer copies
+        comm_streams = {e["args"].get("stream") for e in ks if e.get("cat") == "gpu_memcpy" and "PtoP" in e["name"].replace(" ", "")}
+        def is_comm(e):
+            return "nccl" in e["name"].lower() or (ex.transport == "ce" and e["args"].get("stream") in comm_streams)
+        nccl = [e for e in ks if is_comm(e)]
+        comp = [e for e in ks if not is_comm(e)]
+        sizes = "/".join(f"{sum(g.numel() for g in grads) * 4 / 2 ** 20:.0f}" for _, grads in ex.segments)
+        print(f"transport {ex.transport}, segments (MB) {sizes}")
         end_all = max(e["ts"] + e["dur"] for e in ks)
         end_comp = max(e["ts"] + e["dur"] for e in comp)
         print(f"{world} GPUs: step span {(end_all - t0) / 1e3:.3f} ms, compute ends at {(end_comp - t0) / 1e3:.3f} ms, "
@@ -85,7 +95,12 @@ def main():
         print(f"  compute busy (union) {busy_c / 1e3:.3f} ms, NCCL busy (union) {busy_n / 1e3:.3f} ms, "
               f"NCCL with no compute kernel in flight {exposed / 1e3:.3f} ms")
         for i, e in enumerate(nccl):
-            print(f"  nccl[{i}] {e['name'][:48]:48s} start {(e['ts'] - t0) / 1e3:7.3f} ms  dur {e['dur'] / 1e3:7.3f} ms")
+            if e["dur"] >= 20 or "nccl" in e["name"].lower():
+                print(f"  comm[{i}] {e['name'][:48]:48s} start {(e['ts'] - t0) / 1e3:7.3f} ms  dur {e['dur'] / 1e3:7.3f} ms")
+        # when did the gradients become final?  the gather copies of each segment start right after its events fire
+        gath = [e for e in ks if "multi_tensor_apply" in e["name"] or "foreach" in e["name"].lower()]
+        for e in gath[:40]:
+            print(f"  gather {e['name'][:40]:40s} start {(e['ts'] - t0) / 1e3:7.3f} ms  dur {e['dur'] / 1e3:7.3f} ms")
     else:
         st.run()
         torch.cuda.synchronize()

@@ -143,6 +143,27 @@ __device__ __noinline__ void epilogue_scalar(const KParams& p, const YvDrop& dro
     }
 }
 
+// The epilogue's one global READ per element -- the residual, or aux_in for the activations that multiply by a saved
+// tensor -- is fetched for a whole 32x32 chunk (8 float4 per lane) before the accumulator is even complete.  Loaded inside
+// the row loop, each load sat behind the previous row's stores (they may alias), i.e. eight L2 round trips in series
+// per chunk.
+YV_DEVINL bool epilogue_pre_is_aux(int act) { return act == YV_ACT_MUL_GELU_GRAD || act == YV_ACT_MUL_RELU_MASK; }
+
+YV_DEVINL void epilogue_prefetch(const KParams& p, int lane, int row0, int nc, long long obatch, int split, bool vec_ok,
+                                 float4 (&pre)[8]) {
+    const int n = nc + 4 * (lane & 7);
+    const int r0 = lane >> 3;
+    const float* src = epilogue_pre_is_aux(p.act) ? p.aux_in : (split != 0 ? nullptr : p.residual);
+    if (!(vec_ok && n + 3 < p.N)) src = nullptr;         // (the ragged-edge path loads per element)
+    const int rows_left = p.M - (row0 + r0);
+    const long long ob0 = obatch + (long long)(row0 + r0) * p.ld_out + n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr && 4 * i < rows_left) pre[i] = *reinterpret_cast<const float4*>(src + ob0 + (long long)(4 * i) * p.ld_out);
+    }
+}
+
 // Vector path of the epilogue for the 8 rows x 4 columns this lane owns in a staged 32x32 chunk.  ACT / DROP /
 // SPLITK are compile-time so that a launch only issues the instructions of the features it uses: with run-time
 // tests the compiler predicates the GELU / GELU' / dropout-hash code instead of branching around it, and the
@@ -150,7 +171,7 @@ __device__ __noinline__ void epilogue_scalar(const KParams& p, const YvDrop& dro
 // ACT == -1 selects the run-time generic version (rare feature combinations).
 template <int ACT, bool DROP, bool SPLITK>
 YV_DEVINL void epilogue_rows(const KParams& p, const YvDrop& drop, uint32_t stg, int lane, int row0, int n, int z,
-                             long long obatch, long long pbatch, int split, float4 bias4) {
+                             long long obatch, long long pbatch, int split, float4 bias4, const float4 (&pre)[8]) {
     const int cg = lane & 7;
     const int act = ACT >= 0 ? ACT : p.act;
     const int r0 = lane >> 3;                            // this lane owns rows r0 + 4*i of the chunk
@@ -182,6 +203,9 @@ YV_DEVINL void epilogue_rows(const KParams& p, const YvDrop& drop, uint32_t stg,
     const long long ostep = 4 * p.ld_out, pstep = 4 * p.ld_pl;
     float* const out32 = p.out32;
     float* const aux_out = p.aux_out;
+    // `pre` (epilogue_prefetch) holds aux_in when the activation reads it, else the residual; the other one (both in
+    // one launch: not a combination the step uses) is loaded in the loop
+    const bool pre_aux = epilogue_pre_is_aux(act);
     const float* const aux_in = p.aux_in;
     const float* const residual = (SPLITK && split != 0) ? nullptr : p.residual;
     __nv_bfloat16* const planes = p.out_planes;
@@ -213,17 +237,17 @@ YV_DEVINL void epilogue_rows(const KParams& p, const YvDrop& drop, uint32_t stg,
         }
         if (!SPLITK) {
             if (act == YV_ACT_MUL_GELU_GRAD) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) t = *reinterpret_cast<const float4*>(aux_in + ob);
+                const float4 t = pre[i];
                 x.x *= yv_gelu_grad(t.x); x.y *= yv_gelu_grad(t.y); x.z *= yv_gelu_grad(t.z); x.w *= yv_gelu_grad(t.w);
             } else if (act == YV_ACT_MUL_RELU_MASK) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) t = *reinterpret_cast<const float4*>(aux_in + ob);
+                const float4 t = pre[i];
                 x.x = t.x > 0.f ? x.x : 0.f; x.y = t.y > 0.f ? x.y : 0.f;
                 x.z = t.z > 0.f ? x.z : 0.f; x.w = t.w > 0.f ? x.w : 0.f;
             }
         }
-        if (residual && ok) {
+        if (!pre_aux) {                                  // (zero when there is no residual / the row does not exist)
+            x.x += pre[i].x; x.y += pre[i].y; x.z += pre[i].z; x.w += pre[i].w;
+        } else if (residual && ok) {
             const float4 t = *reinterpret_cast<const float4*>(residual + ob);
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
         }
@@ -262,7 +286,8 @@ YV_DEVINL void epilogue_rows(const KParams& p, const YvDrop& drop, uint32_t stg,
 // (thread = row); it goes through the warp's XOR-swizzled 4 KB staging buffer `stg` so that 8 lanes cover one
 // 128-byte row segment and every global access is coalesced.  row0 = first row of the chunk, nc = first column.
 YV_DEVINL void epilogue_chunk(const KParams& p, const YvDrop& drop, uint32_t stg, int lane, const uint32_t* raw, int row0,
-                              int nc, int z, long long obatch, long long pbatch, int split, bool vec_ok) {
+                              int nc, int z, long long obatch, long long pbatch, int split, bool vec_ok,
+                              const float4 (&pre)[8]) {
     const int cg = lane & 7;                             // float4 column group of this lane inside the chunk
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -279,7 +304,7 @@ YV_DEVINL void epilogue_chunk(const KParams& p, const YvDrop& drop, uint32_t stg
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             const bool drop_on = drop.thresh != 0;
-#define YV_EPI(A, D, S) epilogue_rows<A, D, S>(p, drop, stg, lane, row0, n, z, obatch, pbatch, split, bias4)
+#define YV_EPI(A, D, S) epilogue_rows<A, D, S>(p, drop, stg, lane, row0, n, z, obatch, pbatch, split, bias4, pre)
             if (p.splits > 1) {
                 if (drop_on) YV_EPI(YV_ACT_NONE, true, true); else YV_EPI(YV_ACT_NONE, false, true);
             } else if (p.act == YV_ACT_NONE) {

@@ -241,6 +241,10 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                               (uintptr_t)p.bias) & 15) == 0 && (((uintptr_t)p.out_planes) & 7) == 0;
         const long long obatch = (long long)b0 * p.out_sb0 + (long long)b1 * p.out_sb1;
         const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
+        // residual / aux_in of the first chunk: in flight while the main loop is still running
+        float4 pre[8];
+        if (m0 + q * 32 < p.M && n0 + half * cpw * 32 < p.N)
+            epilogue_prefetch(p, lane, m0 + q * 32, n0 + half * cpw * 32, obatch, split, vec_ok, pre);
         mbar_wait(tmem_full_bar, 0);
         if (threadIdx.x == 64) YV_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -252,7 +256,9 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (nc >= p.N) break;                        // warp-uniform
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok);
+                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok, pre);
+                if (cc + 1 < cpw && nc + 32 < p.N)
+                    epilogue_prefetch(p, lane, m0 + q * 32, nc + 32, obatch, split, vec_ok, pre);
             }
         }
     }

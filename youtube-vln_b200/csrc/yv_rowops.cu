@@ -1391,6 +1391,40 @@ extern "C" int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5,
     YV_LAUNCHED();
 }
 
+// ------------------------------------------------------------------------------------------- exchange: chunk mean
+// out[i] = (sum over ranks r = 0..world-1, in that order, of x_r[i]) / world, where x_rank is `own` (also the output)
+// and x_r of a peer is the row of `stage` the copy engines filled for it: peer (rank - step) mod world sits in row step-1.
+// Streaming, 16 bytes per lane, a bounded grid (the backward pass is running on the same SMs).
+__global__ void __launch_bounds__(512) mean_chunks_kernel(float* __restrict__ own, const float* __restrict__ stage,
+                                                          long long stage_stride, int world, int rank, long long n4) {
+    yv_pdl_wait();
+    const float inv = 1.0f / (float)world;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+            const float* src = r == rank ? own : stage + (long long)(((rank - r + world) % world) - 1) * stage_stride;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
+            if (r == 0) acc = v;
+            else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        }
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+        reinterpret_cast<float4*>(own)[i] = acc;
+    }
+}
+
+extern "C" int yv_mean_chunks(float* own, const float* stage, int64_t stage_stride, int32_t world, int32_t rank, int64_t n,
+                              yv_stream_t stream) {
+    YV_CHECK(own && world >= 1 && rank >= 0 && rank < world && n > 0, "yv_mean_chunks: bad arguments");
+    YV_CHECK(world == 1 || stage, "yv_mean_chunks: no staging rows");
+    YV_CHECK((n & 3) == 0 && (stage_stride & 3) == 0 && (((uintptr_t)own | (uintptr_t)stage) & 15) == 0,
+             "yv_mean_chunks: chunks must be 16-byte aligned multiples of 4 elements");
+    const long long n4 = n / 4;
+    const unsigned blocks = (unsigned)(n4 < 74 * 512 ? (n4 + 511) / 512 : 74);
+    YV_CUDA(yv_launch(mean_chunks_kernel, dim3(blocks), dim3(512), 0, S(stream), own, stage, (long long)stage_stride,
+                      (int)world, (int)rank, n4));
+    YV_LAUNCHED();
+}
+
 extern "C" int yv_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out, int32_t accumulate,
                          yv_stream_t stream) {
     YV_CHECK(x && out && rows > 0 && cols > 0, "yv_colsum: bad arguments");

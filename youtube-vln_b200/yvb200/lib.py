@@ -23,7 +23,7 @@ SYMBOLS = [
     "yv_rng_advance", "yv_layernorm_fwd", "yv_layernorm_bwd", "yv_layernorm_bwd_dx", "yv_layernorm_bwd_cols", "yv_softmax_fwd", "yv_softmax_bwd",
     "yv_embed_text_fwd", "yv_embed_text_bwd", "yv_embed_loc_fwd", "yv_embed_loc_bwd", "yv_colsum",
     "yv_colsum_planes", "yv_act_bwd_split", "yv_adamw_multi", "yv_ce_loss", "yv_ce_grad", "yv_kl_loss", "yv_kl_grad",
-    "yv_mask_tokens", "yv_mask_regions", "yv_attn_supported", "yv_attn_fwd", "yv_attn_bwd", "yv_attn_bwd_workspace_bytes",
+    "yv_mask_tokens", "yv_mask_regions", "yv_attn_supported", "yv_attn_fwd", "yv_attn_bwd", "yv_attn_bwd_workspace_bytes", "yv_mean_chunks",
 ]
 
 
@@ -302,6 +302,19 @@ def embed_loc_bwd(loc, dout, dw5, db5, dw4, db4, dw2, db2, dseq, M, H):
 def colsum(x, ld, rows, cols, out, accumulate=False):
     _check(load().yv_colsum(C.c_void_p(x.data_ptr()), C.c_int64(ld), C.c_int64(rows), C.c_int32(cols),
                             C.c_void_p(out.data_ptr()), C.c_int32(1 if accumulate else 0), _stream()), "colsum")
+
+
+def mean_chunks(own: torch.Tensor, stage: Optional[torch.Tensor], world: int, rank: int):
+    """own <- mean over the ranks (summed in rank order) of own and the ``world - 1`` staged peer copies (gradient
+    exchange over peer-to-peer copies: row step-1 of ``stage`` came from rank (rank - step) mod world)."""
+    if not (own.is_cuda and own.is_contiguous() and own.dtype == torch.float32):
+        raise RuntimeError("mean_chunks: needs a contiguous CUDA float32 chunk")
+    if stage is not None and not (stage.is_cuda and stage.dtype == torch.float32 and stage.stride(1) == 1
+                                  and stage.shape[1] >= own.numel() and stage.shape[0] >= world - 1):
+        raise RuntimeError("mean_chunks: staging rows do not cover the chunk")
+    _check(load().yv_mean_chunks(C.c_void_p(own.data_ptr()), C.c_void_p(_p(stage)),
+                                 C.c_int64(stage.stride(0) if stage is not None else 0), C.c_int32(world), C.c_int32(rank),
+                                 C.c_int64(own.numel()), _stream()), "mean_chunks")
 
 
 def colsum_planes(p: Planes, out, accumulate=False):

@@ -90,7 +90,14 @@ class Runtime:
         self.ln_split = os.environ.get("YVB200_LN_SPLIT", "1") != "0"
         self.want_probs: Optional[bool] = None
         self._tickets: Dict[int, torch.Tensor] = {}
-        prio = os.environ.get("YVB200_PRIORITIES", "1") != "0"
+        # weight-gradient sinks registered by a GradientExchange plan (step.py): {address of the weight's planes:
+        # ([rows, cols] view of the flat exchange buffer, the parameters it covers)} -- see ``_dw_out``
+        self.grad_sink: Dict[int, Tuple[torch.Tensor, tuple]] = {}
+        # YVB200_PRIORITIES=1: the backward chain on high-priority streams, trailing weight-gradient work on low-priority
+        # ones.  Off by default since round 2: on one GPU the two settings measure the same (9.32 vs 9.35 ms, three
+        # alternations), with a gradient exchange the low-priority weight gradients finish so late that the collectives
+        # cannot start before ~70 % of the step (2 GPUs 11.0 -> 10.74 ms, 8 GPUs 11.70 -> 11.30 ms with equal priorities)
+        prio = os.environ.get("YVB200_PRIORITIES", "0") != "0"
         self.main_priority = -1 if prio else 0
         self.helper_priority = 0
         self.branch_stream = torch.cuda.Stream(device=device, priority=self.main_priority)
@@ -497,6 +504,20 @@ class _EarlyOut:
         return self.zeroed
 
 
+def _dw_out(r: "Runtime", wp: "Planes", N: int, K: int, device) -> torch.Tensor:
+    """Where the gradient of the weight(s) behind the planes ``wp`` is written: straight into its slot of the data-parallel
+    exchange buffer when a GradientExchange plan registered one (autograd then adopts that view as ``.grad`` and the
+    exchange has nothing to copy), else a fresh tensor.  Never when a parameter already holds a gradient (accumulation
+    would then add the buffer to itself)."""
+    if r.grad_sink:
+        slot = r.grad_sink.get(wp.addr)
+        if slot is not None:
+            t, params = slot
+            if t.shape[0] == N and t.shape[1] == K and all(q.grad is None for q in params):
+                return t.view(N, K)                  # (a fresh view object: autograd only adopts unshared tensors)
+    return _f32(N, K, device=device)
+
+
 def _keep_for(side: torch.cuda.Stream, *objs):
     """Tensors consumed (or produced) by work left running on ``side``: the caching allocator must not hand their
     memory to a later allocation of the issuing stream before that work has run."""
@@ -540,7 +561,7 @@ def _linear_bwd(r: Runtime, dp: Planes, xp: Optional[Planes], wp: Planes, M: int
         else:
             dx = _f32(M, K, device=device)
     if need_dw:
-        dW = _f32(N, K, device=device)
+        dW = _dw_out(r, wp, N, K, device)
         if not have_db:
             db = _f32(N, device=device)
     fork = r.concurrent and need_dx and need_dw
@@ -976,7 +997,7 @@ class AttnBlockFn(Function):
         acc = r.zeros(3, H)                                               # dgamma, dbeta, d(out bias)
         dz2 = _c2d(dz)
         cols = _ln_bwd_chain(r, dz2, s, gamma, stats, ds, dsp, acc, M, H, spec.out_drop_p, spec.out_site, ctx.rng)
-        dWo = _f32(H, H, device=dev)
+        dWo = _dw_out(r, wo, H, H, dev)
         dOp = Planes.empty(M, H, dev)
         cur = torch.cuda.current_stream(dev)
         side = (r.helper() if r.defer_wgrad else r.fork()) if r.concurrent else cur
@@ -1067,8 +1088,8 @@ class FFNFn(Function):
         acc = r.zeros(3, H)                                               # dgamma, dbeta, db2
         dz2 = _c2d(dz)
         cols = _ln_bwd_chain(r, dz2, s, gamma, stats, ds, dsp, acc, M, H, spec.drop_p, spec.site, ctx.rng)
-        dW2 = _f32(H, FF, device=dev)
-        dW1 = _f32(FF, H, device=dev)
+        dW2 = _dw_out(r, w2, H, FF, dev)
+        dW1 = _dw_out(r, w1, FF, H, dev)
         db1 = _f32(FF, device=dev)
         dprep = Planes.empty(M, FF, dev)
         cur = torch.cuda.current_stream(dev)
