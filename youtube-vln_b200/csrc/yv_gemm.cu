@@ -243,7 +243,8 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
             // residual / aux_in of the first chunk: in flight while the main loop is still running
             float4 pre[8];
-            if (n0 + half * 64 < p.N) epilogue_prefetch(p, lane, m0 + q * 32, n0 + half * 64, obatch, split, vec_ok, pre);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + half * 64 < p.N) epilogue_prefetch(p, lane, m0 + q * 32, n0 + half * 64, obatch, split, vec_ok, pre, bias4);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             if (threadIdx.x == 64) YV_T(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -255,8 +256,8 @@ yv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), raw);
                 YV_T64(8);
-                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok, pre);
-                if (cc == 0 && nc + 32 < p.N) epilogue_prefetch(p, lane, m0 + q * 32, nc + 32, obatch, split, vec_ok, pre);
+                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok, pre, bias4);
+                if (cc == 0 && nc + 32 < p.N) epilogue_prefetch(p, lane, m0 + q * 32, nc + 32, obatch, split, vec_ok, pre, bias4);
             }
             // this warp has finished reading its TMEM lanes of accumulator `acc`: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -144,17 +144,19 @@ __device__ __noinline__ void epilogue_scalar(const KParams& p, const YvDrop& dro
 }
 
 // The epilogue's one global READ per element -- the residual, or aux_in for the activations that multiply by a saved
-// tensor -- is fetched for a whole 32x32 chunk (8 float4 per lane) before the accumulator is even complete.  Loaded inside
+// tensor -- and the bias are fetched for a whole 32x32 chunk (8 float4 per lane) before the accumulator is even complete.  Loaded inside
 // the row loop, each load sat behind the previous row's stores (they may alias), i.e. eight L2 round trips in series
 // per chunk.
 YV_DEVINL bool epilogue_pre_is_aux(int act) { return act == YV_ACT_MUL_GELU_GRAD || act == YV_ACT_MUL_RELU_MASK; }
 
 YV_DEVINL void epilogue_prefetch(const KParams& p, int lane, int row0, int nc, long long obatch, int split, bool vec_ok,
-                                 float4 (&pre)[8]) {
+                                 float4 (&pre)[8], float4& bias4) {
     const int n = nc + 4 * (lane & 7);
     const int r0 = lane >> 3;
     const float* src = epilogue_pre_is_aux(p.act) ? p.aux_in : (split != 0 ? nullptr : p.residual);
+    bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!(vec_ok && n + 3 < p.N)) src = nullptr;         // (the ragged-edge path loads per element)
+    else if (p.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     const int rows_left = p.M - (row0 + r0);
     const long long ob0 = obatch + (long long)(row0 + r0) * p.ld_out + n;
 #pragma unroll
@@ -287,7 +289,7 @@ YV_DEVINL void epilogue_rows(const KParams& p, const YvDrop& drop, uint32_t stg,
 // 128-byte row segment and every global access is coalesced.  row0 = first row of the chunk, nc = first column.
 YV_DEVINL void epilogue_chunk(const KParams& p, const YvDrop& drop, uint32_t stg, int lane, const uint32_t* raw, int row0,
                               int nc, int z, long long obatch, long long pbatch, int split, bool vec_ok,
-                              const float4 (&pre)[8]) {
+                              const float4 (&pre)[8], const float4 bias4) {
     const int cg = lane & 7;                             // float4 column group of this lane inside the chunk
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -301,8 +303,6 @@ YV_DEVINL void epilogue_chunk(const KParams& p, const YvDrop& drop, uint32_t stg
     const int n = nc + 4 * cg;
     if (n < p.N) {
         if (vec_ok && (n + 3 < p.N)) {
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && split == 0) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             const bool drop_on = drop.thresh != 0;
 #define YV_EPI(A, D, S) epilogue_rows<A, D, S>(p, drop, stg, lane, row0, n, z, obatch, pbatch, split, bias4, pre)
             if (p.splits > 1) {

@@ -243,8 +243,9 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const long long pbatch = (long long)b0 * p.pl_sb0 + (long long)b1 * p.pl_sb1;
         // residual / aux_in of the first chunk: in flight while the main loop is still running
         float4 pre[8];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m0 + q * 32 < p.M && n0 + half * cpw * 32 < p.N)
-            epilogue_prefetch(p, lane, m0 + q * 32, n0 + half * cpw * 32, obatch, split, vec_ok, pre);
+            epilogue_prefetch(p, lane, m0 + q * 32, n0 + half * cpw * 32, obatch, split, vec_ok, pre, bias4);
         mbar_wait(tmem_full_bar, 0);
         if (threadIdx.x == 64) YV_T(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -256,9 +257,9 @@ yv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (nc >= p.N) break;                        // warp-uniform
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok, pre);
+                epilogue_chunk(p, drop, stg, lane, raw, m0 + q * 32, nc, z, obatch, pbatch, split, vec_ok, pre, bias4);
                 if (cc + 1 < cpw && nc + 32 < p.N)
-                    epilogue_prefetch(p, lane, m0 + q * 32, nc + 32, obatch, split, vec_ok, pre);
+                    epilogue_prefetch(p, lane, m0 + q * 32, nc + 32, obatch, split, vec_ok, pre, bias4);
             }
         }
     }
