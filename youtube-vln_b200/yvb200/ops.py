@@ -98,8 +98,13 @@ class Runtime:
         # alternations), with a gradient exchange the low-priority weight gradients finish so late that the collectives
         # cannot start before ~70 % of the step (2 GPUs 11.0 -> 10.74 ms, 8 GPUs 11.70 -> 11.30 ms with equal priorities)
         prio = os.environ.get("YVB200_PRIORITIES", "0") != "0"
-        self.main_priority = -1 if prio else 0
-        self.helper_priority = 0
+        # All compute streams sit one level above the default priority so that the start-of-step weight refresh (its
+        # own stream, default priority, 10k-CTA streaming launches) cannot hold the first forward kernels back: with
+        # everything at one level the work distributor dispatched whole refresh chunks ahead of them (split_multi
+        # "running alone" 0.31 ms per step against 0.09 ms).  YVB200_BASE_PRIORITY=0 restores the single level.
+        base = int(os.environ.get("YVB200_BASE_PRIORITY", "-1"))
+        self.helper_priority = base
+        self.main_priority = base - 1 if prio else base
         self.branch_stream = torch.cuda.Stream(device=device, priority=self.main_priority)
 
     # ---- deferred weight-gradient work -------------------------------------------------------------

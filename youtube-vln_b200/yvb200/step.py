@@ -89,7 +89,8 @@ class GradientExchange:
             self.transport = "nccl"
         # (copy-engine transport: its few tiny kernels -- barriers, the chunk mean -- must not queue behind the backward
         # pass; NCCL's channel CTAs keep the default priority)
-        self.comm = torch.cuda.Stream(device=self.device, priority=-1 if self.transport == "ce" else 0) if self.cuda else None
+        base = ops.rt(self.device).helper_priority if self.cuda else 0      # (the level of the trailing compute streams)
+        self.comm = torch.cuda.Stream(device=self.device, priority=base - 1 if self.transport == "ce" else base) if self.cuda else None
         # direct (YVB200_EXCHANGE_DIRECT=1): planned passes write weight gradients straight into the flat buffer instead
         # of copying them there before the collective.  Opt-in: it removes ~0.8 ms of copy kernels per step, but on 2
         # GPUs the step was not faster (the collectives then start earlier and their channel CTAs overlap more of the
@@ -286,7 +287,7 @@ class GradientExchange:
         if self._stage is None or self._stage.shape[1] < n:
             self._stage = torch.empty(self.world - 1, n, dtype=torch.float32, device=self.device)
         if self._copy2 is None:
-            self._copy2 = torch.cuda.Stream(device=self.device, priority=-1)
+            self._copy2 = torch.cuda.Stream(device=self.device, priority=self.comm.priority)
 
     def _build_flat(self):
         """Observed pass (no plan yet, or the plan did not fit): a throw-away flat buffer in arrival order; every
