@@ -37,3 +37,58 @@ def test_ce_phases_average_every_slice(world):
     for r in range(world):
         assert torch.equal(buckets[r], buckets[0])             # bit-identical on every rank
     assert float((buckets[0].double() - want).abs().max()) < 1e-6
+
+
+def _one_rank_group():
+    import socket
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return False
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    return True
+
+
+def test_plan_is_frozen_after_the_first_pass_and_followed():
+    """One rank (gloo, CPU): the first pass is observed, the plan reproduces its segmentation, later passes land in
+    fixed views of one flat buffer and leave the (one-rank) gradients unchanged; shrinking segments keep every
+    parameter exactly once."""
+    import torch.distributed as dist
+    mine = _one_rank_group()
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(*[torch.nn.Linear(64, 64) for _ in range(12)])
+        x = torch.randn(8, 64)
+        ex = GE(net, segment_mb=64 * 64 * 4 * 2.5 / 2 ** 20)          # a segment closes every third weight or so
+
+        def one_pass():
+            net.zero_grad()
+            ex.begin()
+            net(x).square().mean().backward()
+            ex.end()
+            local = {n: p.grad.clone() for n, p in net.named_parameters()}
+            ex.exchange()
+            return local
+
+        one_pass()
+        assert ex._pass_plan is None and ex.plan is not None           # observed; plan frozen at its end
+        observed = [len(g) for _, g in ex.segments]
+        assert [len(s) for s in ex.plan.segments] == observed and len(observed) >= 4
+        local = one_pass()
+        assert ex._pass_plan is ex.plan
+        base = ex.plan.bucket.untyped_storage().data_ptr()
+        for n, p in net.named_parameters():
+            assert p.grad.untyped_storage().data_ptr() == base
+            assert torch.equal(p.grad, local[n])
+        # shrinking rule: target = half of what is still to come, never below the minimum, never above the maximum
+        ex.segment_min_bytes = 64 * 4
+        segs = ex._planned_segments(ex.plan.order)
+        sizes = [sum(q.numel() * 4 for q in s) for s in segs]
+        assert sum(len(s) for s in segs) == len(ex.plan.order) and len(segs) > len(observed)
+        assert sizes[0] >= sizes[len(sizes) // 2] and max(sizes) <= ex.segment_bytes + 64 * 64 * 4
+        ex.remove()
+    finally:
+        if mine:
+            dist.destroy_process_group()
