@@ -803,10 +803,15 @@ __global__ void embed_loc_fwd_kernel(const float* __restrict__ loc, const float*
 }
 
 constexpr int LOC_ROWS = 32;
-__global__ void embed_loc_bwd_kernel(const float* __restrict__ loc, const float* __restrict__ dout, float* __restrict__ dw5,
-                                     float* __restrict__ db5, float* __restrict__ dw4, float* __restrict__ db4,
-                                     float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dseq, long long M,
-                                     int H) {
+constexpr int LOC_SPLIT = 2;                   // CTAs per row block (each owns H / LOC_SPLIT columns): 144 CTAs at cfg2
+// One CTA: 32 rows x a column range.  The frame-embedding gradient (dseq) is accumulated in registers for as long as
+// consecutive rows belong to the same frame (rows arrive frame by frame: one reduction per run instead of one per row --
+// the per-row reductions were most of the kernel's 67 us at the very end of the backward chain).
+__global__ void __launch_bounds__(256)
+embed_loc_bwd_kernel(const float* __restrict__ loc, const float* __restrict__ dout, float* __restrict__ dw5,
+                     float* __restrict__ db5, float* __restrict__ dw4, float* __restrict__ db4,
+                     float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dseq, long long M,
+                     int H) {
     yv_pdl_trigger();
     yv_pdl_wait();
     __shared__ float l[LOC_ROWS][12];
@@ -814,18 +819,28 @@ __global__ void embed_loc_bwd_kernel(const float* __restrict__ loc, const float*
     const int nr = (int)min((long long)LOC_ROWS, M - r0);
     for (int i = threadIdx.x; i < nr * 12; i += blockDim.x) l[i / 12][i % 12] = loc[r0 * 12 + i];
     __syncthreads();
-    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const int hs = (H + LOC_SPLIT - 1) / LOC_SPLIT;
+    const int h1 = min(H, (int)(blockIdx.y + 1) * hs);
+    for (int h = blockIdx.y * hs + threadIdx.x; h < h1; h += blockDim.x) {
         float acc[11];
 #pragma unroll
         for (int j = 0; j < 11; ++j) acc[j] = 0.f;
-        float accb = 0.f;
+        float accb = 0.f, accs = 0.f;
+        int cur = (int)l[0][11];
         for (int r = 0; r < nr; ++r) {
             const float g = dout[(r0 + r) * H + h];
             accb += g;
 #pragma unroll
             for (int j = 0; j < 11; ++j) acc[j] += g * l[r][j];
-            atomicAdd(dseq + (long long)l[r][11] * H + h, g);
+            const int si = (int)l[r][11];
+            if (si != cur) {                                 // (block-uniform)
+                atomicAdd(dseq + (long long)cur * H + h, accs);
+                accs = 0.f;
+                cur = si;
+            }
+            accs += g;
         }
+        atomicAdd(dseq + (long long)cur * H + h, accs);
 #pragma unroll
         for (int j = 0; j < 5; ++j) atomicAdd(dw5 + h * 5 + j, acc[j]);
 #pragma unroll
@@ -1386,7 +1401,7 @@ extern "C" int yv_embed_loc_fwd(const float* loc, const float* w5, const float* 
 extern "C" int yv_embed_loc_bwd(const float* loc, const float* dout, float* dw5, float* db5, float* dw4, float* db4, float* dw2,
                                 float* db2, float* dseq, int64_t M, int32_t H, yv_stream_t stream) {
     YV_CHECK(loc && dout && dw5 && db5 && dw4 && db4 && dw2 && db2 && dseq && M > 0, "yv_embed_loc_bwd: bad arguments");
-    YV_CUDA(yv_launch(embed_loc_bwd_kernel, dim3((unsigned)((M + LOC_ROWS - 1) / LOC_ROWS)), dim3(256), 0, S(stream), loc, dout, dw5, db5, dw4, db4, dw2,
+    YV_CUDA(yv_launch(embed_loc_bwd_kernel, dim3((unsigned)((M + LOC_ROWS - 1) / LOC_ROWS), LOC_SPLIT), dim3(256), 0, S(stream), loc, dout, dw5, db5, dw4, db4, dw2,
                                                                                           db2, dseq, M, H));
     YV_LAUNCHED();
 }

@@ -1261,11 +1261,21 @@ class TextEmbedFn(Function):
         de = _f32(M, H, device=dev)
         acc = r.zeros(2, H)
         dgamma, dbeta = acc[0], acc[1]
+        # these are the last kernels of the backward chain: the 94 MB zero fill of the word-embedding gradient runs on a
+        # forked stream next to the LayerNorm backward instead of after it
+        dword = torch.empty(ctx.shapes[0], dtype=torch.float32, device=dev)
+        dpos = torch.empty(ctx.shapes[1], dtype=torch.float32, device=dev)
+        dtyp = torch.empty(ctx.shapes[2], dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side = r.fork(2) if r.concurrent else cur
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            dword.zero_()
+            dpos.zero_()
+            dtyp.zero_()
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, None, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
                         post_drop_site=spec.site, rng=ctx.rng)
-        dword = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dev)
-        dpos = torch.zeros(ctx.shapes[1], dtype=torch.float32, device=dev)
-        dtyp = torch.zeros(ctx.shapes[2], dtype=torch.float32, device=dev)
+        cur.wait_stream(side)
         L.embed_text_bwd(tok, seg, de, dword, dpos, dtyp, M, T, H, spec.padding_idx)
         return None, None, dword, dpos, dtyp, dgamma, dbeta, None
 
@@ -1319,8 +1329,14 @@ class ImageEmbedFn(Function):
         L.layernorm_bwd(_c2d(dy), e, gamma, stats, de, dep, dgamma, dbeta, M, H, post_drop_p=spec.drop_p,
                         post_drop_site=spec.site, rng=ctx.rng, dbias=acc[2])
         dfeat, dWi, dbi = _linear_bwd(r, dep, ctx.fp, ctx.wp, M, H, F, dev, ctx.needs_input_grad[0], True, db=acc[2])
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)  # noqa: E731
-        dw5, db5, dw4, db4, dw2, db2, dseq = z(H, 5), z(H), z(H, 4), z(H), z(H, 2), z(H), z(32, H)
+        # the seven small accumulators of the location / frame embeddings come out of the pass's zero slab (no fill kernels
+        # at the very end of the backward chain): H x (5 + 1 + 4 + 1 + 2 + 1) floats and the [32, H] frame table
+        zb = r.zeros(46, H).view(-1)
+        cuts, off = [], 0
+        for n_, shape in ((5 * H, (H, 5)), (H, (H,)), (4 * H, (H, 4)), (H, (H,)), (2 * H, (H, 2)), (H, (H,)), (32 * H, (32, H))):
+            cuts.append(zb[off:off + n_].view(shape))
+            off += n_
+        dw5, db5, dw4, db4, dw2, db2, dseq = cuts
         L.embed_loc_bwd(loc2, de, dw5, db5, dw4, db4, dw2, db2, dseq, M, H)
         return ((dfeat.view(pairs, V, F) if dfeat is not None else None), None, dWi, dbi, dw5, db5, dw4, db4, dw2, db2,
                 dseq, dgamma, dbeta, None)
